@@ -1,0 +1,125 @@
+/* sd3d.h -- C ABI of libsd3d.so: the B200 (sm_100a) implementation of SegDINO3D's 2D->3D feature
+ * lifting + superpoint pooling + mask-logit path.
+ *
+ * Boundary rules:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller (PyTorch) owns and allocates every buffer, including outputs and workspaces; the
+ *     library never allocates, frees or retains a pointer past return;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - every entry returns SD3D_OK or a negative code; sd3d_last_error() gives the thread-local text;
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns SD3D_ERR_CUDA.
+ *
+ * Each entry cites the reference interface it replaces (paths relative to /root/reference).
+ */
+#ifndef SD3D_H_
+#define SD3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD3D_VERSION 100
+
+#define SD3D_OK 0
+#define SD3D_ERR_ARG (-1)         /* null pointer, negative size, misaligned buffer, workspace too small */
+#define SD3D_ERR_UNSUPPORTED (-2) /* shape / dtype outside what the kernels are specialised for */
+#define SD3D_ERR_CUDA (-3)        /* CUDA launch / runtime error (text in sd3d_last_error) */
+
+/* element type codes */
+#define SD3D_F32 0
+#define SD3D_F16 1
+#define SD3D_BF16 2
+#define SD3D_U16 3 /* depth only: ScanNet uint16 millimetres, d = (float)raw * 0.001f */
+
+/* sd3d_sp_mean / sd3d_lift modes */
+#define SD3D_POOL_FAST 0  /* run-partials + ordered combine: deterministic, <=1e-5 rel. of the oracle */
+#define SD3D_POOL_EXACT 1 /* ascending-point-index summation: bit-identical to aten CPU scatter_add_ */
+
+int sd3d_version(void);
+const char* sd3d_last_error(void);
+/* number of SMs of the current device (grid sizing of the host mirror); <0 on error */
+int sd3d_device_sms(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * a-4 prerequisite: stable counting sort of points by superpoint id.
+ * Replaces the implicit grouping inside torch_scatter.scatter_mean(src, index, dim=0)
+ *   segdino3d/models/backbone/spconvunet.py:390,392 ; minkunet.py:639,641 (index = int64 ids).
+ * idx[N] int64 ids in [0,S) (ids outside that range are parked after seg_offsets[S] and ignored).
+ * perm[N] int32: point indices, superpoint by superpoint, ascending point index inside each.
+ * seg_offsets[S+1] int32: superpoint s owns perm[seg_offsets[s] .. seg_offsets[s+1]).
+ * --------------------------------------------------------------------------------------------- */
+size_t sd3d_sp_sort_workspace_bytes(int64_t N, int64_t S);
+int sd3d_sp_sort(const int64_t* idx, int64_t N, int64_t S, int32_t* perm, int32_t* seg_offsets, void* ws,
+                 size_t ws_bytes, void* stream);
+
+/* Splits every superpoint into runs of <= `run` consecutive sorted points (the unit one warp reduces).
+ * task_offsets[S+1]: superpoint s owns tasks [task_offsets[s], task_offsets[s+1]); task_seg[t] = s.
+ * max_tasks = sd3d_sp_max_tasks(N,S,run) is the size the caller must give task_seg. */
+int64_t sd3d_sp_max_tasks(int64_t N, int64_t S, int run);
+int sd3d_sp_tasks(const int32_t* seg_offsets, int64_t S, int run, int32_t* task_offsets, int32_t* task_seg,
+                  int64_t max_tasks, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a-4: out[s,:] = sum_{p in s} src[p,:] / max(|s|,1)    == scatter_mean(src, idx, dim=0)
+ *   spconvunet.py:325,350,390,392 ; minkunet.py:639,641,653,674 ; torch-scatter 2.1.2 scatter_mean.
+ * src[N,C] f32 row-major; perm/seg_offsets from sd3d_sp_sort; out[S,C] f32 fully overwritten.
+ * point_count (nullable): fused lift finalize -- row p is divided by (float)max(point_count[p],1) first.
+ * mode FAST needs task_offsets/task_seg (sd3d_sp_tasks) and ws >= max_tasks*C*4 bytes; EXACT needs none.
+ * --------------------------------------------------------------------------------------------- */
+int sd3d_sp_mean(const float* src, const int32_t* perm, const int32_t* seg_offsets, int64_t N, int64_t S, int C,
+                 const int32_t* point_count, int mode, const int32_t* task_offsets, const int32_t* task_seg,
+                 int64_t max_tasks, int run, void* ws, size_t ws_bytes, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a-1..a-3 (+ optional fused a-4): projection + depth-visibility test, bilinear gather of the
+ * channels-last feature maps, sum over visible views, mean, superpoint pooling.
+ * The reference has NO code for this (features are loaded precomputed,
+ *   segdino3d/datasets/dataset/scannet200.py:219-226 ; scannet.py:177-184); the contract is the frozen
+ *   spec of SURVEY.md Appendix A, whose output feeds extra_features["points_2dfeats"]
+ *   (spconvunet.py:378 ; minkunet.py:612-618).
+ *
+ * xyz[N,3] f32; K4[V,4] f32 (fx,fy,cx,cy); w2c[V,3,4] f32; depth[V,Hd,Wd] (SD3D_F32 metres | SD3D_U16 mm);
+ * fmap[V,Hf,Wf,C] channels-last (SD3D_F32 | SD3D_F16 | SD3D_BF16), C % 4 == 0 (C % 8 for 16-bit), C <= 1024.
+ * view_begin/view_end: the ascending view range [view_begin, view_end) this call sums (a multi-GPU view
+ *   shard); pix_idx/vis rows outside it are not touched.
+ * accumulate != 0: start from the (sum,count) already in out_feat / count (continues the view loop of a
+ *   previous call bit-exactly); finalize != 0: out_feat = sum / (float)max(count,1), else the raw sum.
+ * order (nullable) int32[N]: processing order (perm from sd3d_sp_sort; spatially coherent order makes
+ *   the gather cache-friendly). Results do not depend on it.
+ * pix_idx[V,N] int32 (wi*Wd+ui or -1) and vis[V,N] u8: nullable parity outputs.
+ * Fused pooling (sp_out != NULL): needs order/seg_offsets/task_offsets/task_seg/run from the plan
+ *   entries above, finalize != 0, ws >= max_tasks*C*4 bytes; sp_out[S,C] = scatter_mean(out_feat, idx).
+ * --------------------------------------------------------------------------------------------- */
+int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin, int view_end,
+              const void* depth, int depth_dtype, int Hd, int Wd, const void* fmap, int fmap_dtype, int Hf, int Wf,
+              int C, float stride, float tau, float z_near, int accumulate, int finalize, const int32_t* order,
+              float* out_feat, int32_t* count, int32_t* pix_idx, uint8_t* vis, const int32_t* seg_offsets,
+              int64_t S, const int32_t* task_offsets, const int32_t* task_seg, int64_t max_tasks, int run, void* ws,
+              size_t ws_bytes, float* sp_out, int variant, void* stream);
+
+/* feat = sum / (float)max(count,1) in place (Appendix A `feat_l`); used after the multi-GPU all-reduce */
+int sd3d_lift_finalize(float* sum_inout, const int32_t* count, int64_t N, int C, void* stream);
+
+/* out = (a + b + ...)/L over L scales: points_2dfeats = stack(list).mean(0), scannet200.py:233-234 */
+int sd3d_scale_mean(const float* const* feats_host /*host array of L device ptrs*/, int L, int64_t numel,
+                    float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * a-5: pred_mask[n,m] = sum_d q[n,d] * mf[m,d]     == torch.einsum('nd,md->nm', q, mf)
+ *   segdino3d/models/decoder/instance_seg_3d_decoder.py:567 (ScanNetQueryDecoder._forward_head), :339.
+ * q[n,d], mf[S,d] f32 row-major (K-major); out[n,S] f32 row-major.
+ * precision: SD3D_F32  -> fp32 FFMA tiles (<=1e-5 rel.),
+ *            SD3D_BF16 -> operands rounded to bf16, tcgen05.mma kind::f16 with fp32 TMEM accumulators (<=1e-2).
+ * attn_mask (nullable) u8[n,S]: fused epilogue of :568-570 -- sigmoid(pred) < thr; rows that are
+ *   all-true are reset to all-false by sd3d_attn_mask_fix (second tiny launch, done inside this call).
+ * --------------------------------------------------------------------------------------------- */
+int sd3d_mask_logits(const float* q, const float* mf, int n, int S, int d, int precision, float* out,
+                     float thr, uint8_t* attn_mask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SD3D_H_ */

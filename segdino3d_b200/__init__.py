@@ -1,0 +1,11 @@
+"""segdino3d_b200 -- B200 (sm_100a) implementation of SegDINO3D's 2D->3D feature-lifting, superpoint
+pooling and mask-logit path, behind the reference's own operator interface. See DESIGN.md.
+
+Importing the package does not load the CUDA library; the first op call does, and raises if
+libsd3d.so is missing (there is no CPU fallback)."""
+from ._lib import Sd3dError  # noqa: F401
+from .ops import (SuperpointPlan, lift, lift_and_pool, lift_features, lift_finalize, mask_logits,  # noqa: F401
+                  scale_mean, scatter_mean, sp_mean, sp_sort)
+
+__all__ = ["Sd3dError", "SuperpointPlan", "lift", "lift_and_pool", "lift_features", "lift_finalize", "mask_logits",
+           "scale_mean", "scatter_mean", "sp_mean", "sp_sort"]

@@ -1,0 +1,315 @@
+// mask_gemm.cu -- query x superpoint mask logits: out[n,S] = q[n,d] . mf[S,d]^T  (+ fused attention mask).
+//
+// Replaces   pred_mask = torch.einsum('nd,md->nm', norm_query, mask_feats[i])
+//            attn_mask = (pred_mask.sigmoid() < thr); all-true rows reset to all-false
+// at /root/reference/segdino3d/models/decoder/instance_seg_3d_decoder.py:567-571 (and :339-343), which the
+// reference runs as cuBLAS SGEMM + ~5 elementwise/reduce kernels, 7 times per forward.
+//
+// Two precisions behind one entry point:
+//   SD3D_F32  : fp32 FFMA register-tiled kernel, K summed in ascending order (<=1e-5 rel.).
+//   SD3D_BF16 : the one dense contraction of the path -> 5th-gen tensor cores. Both operands are K-major
+//               ("TN"), so each CTA converts its fp32 operand tiles to bf16 straight into the canonical
+//               K-major SWIZZLE_128B shared-memory layout (no transpose, no extra HBM pass), one elected
+//               thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=64, K=16 x d/16) with the fp32
+//               accumulator in TMEM, tcgen05.commit signals an mbarrier, and the four warps read their
+//               32 TMEM lanes back with tcgen05.ld for the epilogue (logits + sigmoid threshold).
+// Tensor-pipe roofline note: 2*n*S*d = 51 MFLOP at the ScanNet200 shape -> launch/latency bound; see DESIGN.md.
+#include "common.cuh"
+
+namespace sd3d {
+
+// ------------------------------------------------------------------------------------------------
+// fp32 path
+// ------------------------------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+    mask_logits_f32_kernel(const float* __restrict__ q, const float* __restrict__ mf, int n, int S, int d,
+                           float* __restrict__ out, float thr, uint8_t* __restrict__ attn) {
+    constexpr int BK = 32;
+    constexpr int NT = (BM / TM) * (BN / TN);
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < d; k0 += BK) {
+        for (int e = tid; e < BM * BK; e += NT) {
+            const int r = e / BK, k = e % BK;
+            const int gm = m0 + r, gk = k0 + k;
+            As[k][r] = (gm < n && gk < d) ? __ldg(q + (int64_t)gm * d + gk) : 0.f;
+        }
+        for (int e = tid; e < BN * BK; e += NT) {
+            const int r = e / BK, k = e % BK;
+            const int gn = n0 + r, gk = k0 + k;
+            Bs[k][r] = (gn < S && gk < d) ? __ldg(mf + (int64_t)gn * d + gk) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[TM], b[TN];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int gm = m0 + ty * TM + i;
+        if (gm >= n) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const int gn = n0 + tx * TN + j;
+            if (gn >= S) continue;
+            const float v = acc[i][j];
+            out[(int64_t)gm * S + gn] = v;
+            if (attn) attn[(int64_t)gm * S + gn] = (1.0f / (1.0f + expf(-v))) < thr ? 1 : 0;
+        }
+    }
+}
+
+// rows whose mask is all-true are reset to all-false (instance_seg_3d_decoder.py:570-571); warp per row
+__global__ void attn_mask_fix_kernel(uint8_t* __restrict__ attn, int n, int S) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = lane_id();
+    uint8_t* r = attn + (int64_t)row * S;
+    int all_true = 1;
+    for (int c = lane; c < S; c += 32) all_true &= (r[c] != 0);
+    all_true = __all_sync(kFull, all_true);
+    if (all_true)
+        for (int c = lane; c < S; c += 32) r[c] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 / TMEM path (bf16 operands, fp32 accumulate)
+// ------------------------------------------------------------------------------------------------
+constexpr int kTcBM = 128;      // UMMA_M
+constexpr int kTcBN = 64;       // UMMA_N (TMEM columns)
+constexpr int kTcThreads = 128; // 4 warps <-> 4 x 32 TMEM lanes
+constexpr int kTcKBlock = 64;   // bf16 elements per 128-byte swizzle row
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format: version=1 at bit 46, layout type 2 at 61)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+    uint64_t desc = 0;
+    desc |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);        // start address, 16-byte units
+    desc |= (uint64_t)1u << 16;                            // leading byte offset (unused for swizzled K-major)
+    desc |= (uint64_t)((1024u >> 4) & 0x3FFFu) << 32;      // stride byte offset: 8 rows x 128 B
+    desc |= (uint64_t)1u << 46;                            // descriptor version (Blackwell)
+    desc |= (uint64_t)2u << 61;                            // LayoutType::SWIZZLE_128B
+    return desc;
+}
+
+// instruction descriptor: kind::f16, A=B=bf16, D=f32, both K-major, M=128, N=kTcBN
+__device__ __forceinline__ uint32_t make_idesc_bf16_f32(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (spin > (1u << 24)) __trap();  // never hang the GPU: a lost commit becomes a reported error
+    }
+}
+
+// Convert a [rows x d] fp32 row-major tile (rows beyond `valid_rows` are zero) to bf16 in the canonical
+// K-major SWIZZLE_128B layout: K-block kb (64 elements) is a [ROWS x 128 B] slab; 16-byte chunk j of row r
+// lands at r*128 + ((j ^ (r & 7)) << 4).
+template <int ROWS>
+__device__ __forceinline__ void stage_operand(const float* __restrict__ g, int64_t row0, int valid_rows, int d,
+                                              uint8_t* smem_tile) {
+    const int chunks_per_row = d >> 3;
+    const int total = ROWS * chunks_per_row;
+    for (int e = threadIdx.x; e < total; e += kTcThreads) {
+        const int r = e / chunks_per_row, kc = e % chunks_per_row;
+        float4 lo = f4_zero(), hi = f4_zero();
+        if (r < valid_rows) {
+            const float* src = g + (row0 + r) * (int64_t)d + kc * 8;
+            lo = ldg_f4(src);
+            hi = ldg_f4(src + 4);
+        }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(lo.x, lo.y), p1 = __floats2bfloat162_rn(lo.z, lo.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(hi.x, hi.y), p3 = __floats2bfloat162_rn(hi.z, hi.w);
+        uint4 packed;
+        packed.x = *reinterpret_cast<uint32_t*>(&p0);
+        packed.y = *reinterpret_cast<uint32_t*>(&p1);
+        packed.z = *reinterpret_cast<uint32_t*>(&p2);
+        packed.w = *reinterpret_cast<uint32_t*>(&p3);
+        const int kb = kc >> 3, j = kc & 7;
+        uint8_t* dst = smem_tile + (size_t)kb * (ROWS * 128) + r * 128 + ((j ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = packed;
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads)
+    mask_logits_tc_kernel(const float* __restrict__ q, const float* __restrict__ mf, int n, int S, int d,
+                          float* __restrict__ out, float thr, uint8_t* __restrict__ attn) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment required by SWIZZLE_128B atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int kblocks = d / kTcKBlock;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)kblocks * (kTcBM * 128);
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * kTcBN;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
+                     "r"((uint32_t)kTcBN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    stage_operand<kTcBM>(q, m0, min(kTcBM, n - m0), d, sA);
+    stage_operand<kTcBN>(mf, n0, min(kTcBN, S - n0), d, sB);
+    // generic-proxy smem writes -> visible to the async proxy (tensor core reads)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = s_tmem;
+
+    if (threadIdx.x == 0) {
+        const uint32_t idesc = make_idesc_bf16_f32(kTcBM, kTcBN);
+        const uint64_t descA0 = make_kmajor_sw128_desc(smem_u32(sA));
+        const uint64_t descB0 = make_kmajor_sw128_desc(smem_u32(sB));
+        for (int kb = 0; kb < kblocks; ++kb) {
+#pragma unroll
+            for (int ks = 0; ks < kTcKBlock / 16; ++ks) {
+                const uint64_t da = descA0 + (uint64_t)(((uint32_t)kb * (kTcBM * 128) + ks * 32) >> 4);
+                const uint64_t db = descB0 + (uint64_t)(((uint32_t)kb * (kTcBN * 128) + ks * 32) >> 4);
+                const uint32_t accumulate = (kb | ks) ? 1u : 0u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "setp.ne.b32 p, %4, 0;\n\t"
+                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                    :
+                    : "r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                    : "memory");
+            }
+        }
+        // commit: arrives on the mbarrier when all MMAs above have completed (implies before_thread_sync)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(&s_bar))
+                     : "memory");
+    }
+    __syncwarp();
+    mbar_wait_parity(smem_u32(&s_bar), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // epilogue: warp w owns TMEM lanes [32w, 32w+32) == accumulator rows; thread = one row, 32 columns per load
+    const int gm = m0 + warp * 32 + lane;
+#pragma unroll
+    for (int c0 = 0; c0 < kTcBN; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (gm < n) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int gn = n0 + c0 + j;
+                if (gn < S) {
+                    const float val = __uint_as_float(v[j]);
+                    out[(int64_t)gm * S + gn] = val;
+                    if (attn) attn[(int64_t)gm * S + gn] = (1.0f / (1.0f + expf(-val))) < thr ? 1 : 0;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTcBN)
+                     : "memory");
+    }
+}
+
+}  // namespace sd3d
+
+using namespace sd3d;
+
+extern "C" int sd3d_mask_logits(const float* q, const float* mf, int n, int S, int d, int precision, float* out,
+                                float thr, uint8_t* attn_mask, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || S < 0 || d <= 0) {
+        set_error("sd3d_mask_logits: bad shape n=%d S=%d d=%d", n, S, d);
+        return SD3D_ERR_ARG;
+    }
+    if (n == 0 || S == 0) return SD3D_OK;
+    if (q == nullptr || mf == nullptr || out == nullptr) {
+        set_error("sd3d_mask_logits: null buffer");
+        return SD3D_ERR_ARG;
+    }
+    if (precision == SD3D_F32) {
+        const bool big = ((int64_t)((n + 63) / 64) * ((S + 63) / 64)) >= 2 * (int64_t)num_sms();
+        if (big) {
+            dim3 grid((S + 63) / 64, (n + 63) / 64);
+            mask_logits_f32_kernel<64, 64, 4, 4><<<grid, 256, 0, stream>>>(q, mf, n, S, d, out, thr, attn_mask);
+        } else {
+            dim3 grid((S + 31) / 32, (n + 31) / 32);
+            mask_logits_f32_kernel<32, 32, 2, 2><<<grid, 256, 0, stream>>>(q, mf, n, S, d, out, thr, attn_mask);
+        }
+    } else if (precision == SD3D_BF16) {
+        if (d % kTcKBlock != 0 || d > 512 || !aligned16(q) || !aligned16(mf)) {
+            set_error("sd3d_mask_logits: tcgen05 path needs d %% 64 == 0, d <= 512 and 16-byte aligned operands (d=%d)",
+                      d);
+            return SD3D_ERR_UNSUPPORTED;
+        }
+        const size_t smem = (size_t)(d / kTcKBlock) * (kTcBM + kTcBN) * 128 + 1024;
+        static bool attr_set = false;  // idempotent attribute; benign race
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(mask_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(512 / kTcKBlock * (kTcBM + kTcBN) * 128 + 1024));
+            if (e != cudaSuccess) {
+                set_error("sd3d_mask_logits: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+                return SD3D_ERR_CUDA;
+            }
+            attr_set = true;
+        }
+        dim3 grid((S + kTcBN - 1) / kTcBN, (n + kTcBM - 1) / kTcBM);
+        mask_logits_tc_kernel<<<grid, kTcThreads, smem, stream>>>(q, mf, n, S, d, out, thr, attn_mask);
+    } else {
+        set_error("sd3d_mask_logits: precision code %d unsupported (SD3D_F32 | SD3D_BF16)", precision);
+        return SD3D_ERR_UNSUPPORTED;
+    }
+    if (attn_mask != nullptr) {
+        attn_mask_fix_kernel<<<(n + 7) / 8, 256, 0, stream>>>(attn_mask, n, S);
+    }
+    return check_launch("sd3d_mask_logits");
+}

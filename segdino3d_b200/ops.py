@@ -1,0 +1,347 @@
+"""Host-side mirror of the reference's operator interface for the lifting / pooling / mask-logit path.
+
+Same names, argument meaning and error behaviour as the torch / torch_scatter operators the reference
+calls (citations relative to /root/reference):
+
+* ``scatter_mean(src, index, dim=-1, out=None, dim_size=None)``   torch_scatter 2.1.2, called as
+  ``scatter_mean(x, sp_ids, dim=0)`` at segdino3d/models/backbone/spconvunet.py:325,350,390,392 and
+  minkunet.py:639,641,653,674.
+* ``mask_logits(q, mf)`` == ``torch.einsum('nd,md->nm', q, mf)``   decoder/instance_seg_3d_decoder.py:567.
+* ``lift_features(...)`` produces the list-over-scales of ``[N,256]`` tensors that the reference loads from
+  ``features_2d/{scene}.pth`` (datasets/dataset/scannet200.py:219-226); the lifting code itself is absent
+  from the reference, the contract is SURVEY.md Appendix A.
+
+All compute goes through the C ABI of libsd3d.so (include/sd3d.h). Inputs must live on a CUDA device;
+there is no CPU fallback -- a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Sd3dError, check
+
+DEFAULT_RUN = 32
+TAU_DEFAULT = 0.05
+Z_NEAR_DEFAULT = 0.1
+
+_FMAP_CODE = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+_DEPTH_CODE = {torch.float32: _lib.F32, torch.uint16: _lib.U16}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(name: str, t: torch.Tensor) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise Sd3dError(f"{name} is on {t.device}: segdino3d_b200 ops run on CUDA only (no CPU fallback)")
+
+
+# ---------------------------------------------------------------------------------------------------
+# superpoint plan: stable sort by superpoint id + run table
+# ---------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class SuperpointPlan:
+    """perm / seg_offsets (+ run table) for one concatenated batch of superpoint ids."""
+    perm: torch.Tensor          # int32 [N]   point ids, superpoint by superpoint, ascending inside each
+    seg_offsets: torch.Tensor   # int32 [S+2] superpoint s owns perm[seg_offsets[s]:seg_offsets[s+1]]; [S:S+2] = invalid ids
+    task_offsets: torch.Tensor  # int32 [S+2]
+    task_seg: torch.Tensor      # int32 [max_tasks]
+    n_points: int
+    n_segments: int
+    run: int
+    max_tasks: int
+
+
+def sp_sort(index: torch.Tensor, n_segments: Optional[int] = None, run: int = DEFAULT_RUN) -> SuperpointPlan:
+    """Stable counting sort of point ids by superpoint id (replaces the implicit grouping of scatter_mean).
+
+    ``n_segments=None`` -> ``int(index.max()) + 1`` exactly like torch_scatter (one host sync, the same
+    ``.max().item()`` the reference does at spconvunet.py:371).
+    """
+    _need_cuda("index", index)
+    if index.dim() != 1:
+        raise ValueError("index must be 1-D")
+    if index.dtype != torch.int64:
+        index = index.to(torch.int64)
+    index = index.contiguous()
+    n = index.numel()
+    if n_segments is None:
+        n_segments = int(index.max().item()) + 1 if n > 0 else 0
+    s = int(n_segments)
+    lib = _lib.load()
+    dev = index.device
+    with torch.cuda.device(dev):
+        perm = torch.empty(n, dtype=torch.int32, device=dev)
+        seg_offsets = torch.empty(s + 2, dtype=torch.int32, device=dev)
+        ws_bytes = int(lib.sd3d_sp_sort_workspace_bytes(n, s))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        check(lib.sd3d_sp_sort(_ptr(index), n, s, _ptr(perm), _ptr(seg_offsets), _ptr(ws), ws_bytes, _stream()),
+              "sd3d_sp_sort")
+        max_tasks = int(lib.sd3d_sp_max_tasks(n, s, run))
+        task_offsets = torch.empty(s + 2, dtype=torch.int32, device=dev)
+        task_seg = torch.empty(max(max_tasks, 1), dtype=torch.int32, device=dev)
+        check(lib.sd3d_sp_tasks(_ptr(seg_offsets), s, run, _ptr(task_offsets), _ptr(task_seg), max_tasks, _stream()),
+              "sd3d_sp_tasks")
+    return SuperpointPlan(perm, seg_offsets, task_offsets, task_seg, n, s, run, max_tasks)
+
+
+def sp_mean(src: torch.Tensor, plan: SuperpointPlan, exact: bool = True,
+            point_count: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[s,:] = mean of src rows of superpoint s (0 for empty ids). ``exact`` = bit-identical to the CPU
+    reference summation order; ``exact=False`` = run partials, deterministic, <=1e-5."""
+    _need_cuda("src", src)
+    if src.dtype != torch.float32:
+        raise Sd3dError(f"sp_mean supports float32 src only (got {src.dtype})")
+    if src.dim() != 2 or src.shape[0] != plan.n_points:
+        raise ValueError(f"src must be [N={plan.n_points}, C], got {tuple(src.shape)}")
+    src = src.contiguous()
+    c = src.shape[1]
+    dev = src.device
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(plan.n_segments, c, dtype=torch.float32, device=dev)
+    elif (not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous()
+          or tuple(out.shape) != (plan.n_segments, c)):
+        raise ValueError("out must be a contiguous CUDA float32 [S,C] tensor")
+    if c == 0 or plan.n_segments == 0:
+        return out
+    if point_count is not None:
+        _need_cuda("point_count", point_count)
+        if point_count.dtype != torch.int32 or point_count.numel() != plan.n_points:
+            raise ValueError("point_count must be int32 [N]")
+        point_count = point_count.contiguous()
+    with torch.cuda.device(dev):
+        if exact:
+            check(lib.sd3d_sp_mean(_ptr(src), _ptr(plan.perm), _ptr(plan.seg_offsets), plan.n_points,
+                                   plan.n_segments, c, _ptr(point_count), _lib.POOL_EXACT, None, None, 0, 0, None, 0,
+                                   _ptr(out), _stream()), "sd3d_sp_mean")
+        else:
+            ws_bytes = plan.max_tasks * c * 4
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            check(lib.sd3d_sp_mean(_ptr(src), _ptr(plan.perm), _ptr(plan.seg_offsets), plan.n_points,
+                                   plan.n_segments, c, _ptr(point_count), _lib.POOL_FAST, _ptr(plan.task_offsets),
+                                   _ptr(plan.task_seg), plan.max_tasks, plan.run, _ptr(ws), ws_bytes, _ptr(out),
+                                   _stream()), "sd3d_sp_mean")
+    return out
+
+
+def scatter_mean(src: torch.Tensor, index: torch.Tensor, dim: int = -1, out: Optional[torch.Tensor] = None,
+                 dim_size: Optional[int] = None, exact: bool = True) -> torch.Tensor:
+    """Drop-in for ``torch_scatter.scatter_mean`` on the reference's call pattern: float32 ``src`` of
+    shape [N] or [N, C], 1-D int64 ``index`` of length N, reduction over dim 0.
+
+    Semantics restated from torch-scatter 2.1.2: output size along ``dim`` is ``dim_size`` or
+    ``index.max()+1``; empty ids give 0 rows; if ``out`` is given the group sums are added to it before the
+    division (torch_scatter's behaviour), which costs one extra elementwise pass here.
+    Anything outside that pattern raises (no silent fallback to another implementation).
+    """
+    _need_cuda("src", src)
+    _need_cuda("index", index)
+    if src.dim() not in (1, 2):
+        raise Sd3dError(f"scatter_mean drop-in covers 1-D / 2-D src (reference call sites); got {src.dim()}-D")
+    d = dim + src.dim() if dim < 0 else dim
+    if d != 0:
+        raise Sd3dError("scatter_mean drop-in covers reduction over dim 0 only (all reference call sites use dim=0)")
+    if index.dim() != 1 or index.shape[0] != src.shape[0]:
+        raise ValueError("index must be 1-D with one id per src row")
+    if not src.is_floating_point():
+        raise Sd3dError("scatter_mean drop-in covers floating-point src only")
+    squeeze = src.dim() == 1
+    src2 = src.reshape(src.shape[0], -1)
+    orig_dtype = src2.dtype
+    if orig_dtype != torch.float32:
+        src2 = src2.float()
+    if out is not None:
+        s = out.shape[0]
+    elif dim_size is not None:
+        s = int(dim_size)
+    elif index.numel() == 0:
+        s = 0
+    else:
+        s = int(index.max().item()) + 1
+    plan = sp_sort(index, s)
+    res = sp_mean(src2, plan, exact=exact)
+    if orig_dtype != torch.float32:
+        res = res.to(orig_dtype)
+    if squeeze:
+        res = res.squeeze(1)
+    if out is not None:
+        # torch_scatter: out.scatter_add_(src) then out /= count  ==  (out + sum) / count
+        counts = (plan.seg_offsets[1:s + 1] - plan.seg_offsets[:s]).clamp(min=1).to(out.dtype)
+        cshape = counts if out.dim() == 1 else counts[:, None]
+        out.copy_(out / cshape + res)
+        return out
+    return res
+
+
+# ---------------------------------------------------------------------------------------------------
+# lifting
+# ---------------------------------------------------------------------------------------------------
+def _check_lift_inputs(xyz, K, w2c, depth, fmap):
+    for name, t in (("xyz", xyz), ("K", K), ("w2c", w2c), ("depth", depth), ("fmap", fmap)):
+        _need_cuda(name, t)
+    if xyz.dtype != torch.float32 or xyz.dim() != 2 or xyz.shape[1] != 3:
+        raise ValueError("xyz must be float32 [N,3]")
+    v = K.shape[0]
+    if K.dtype != torch.float32 or tuple(K.shape) != (v, 4):
+        raise ValueError("K must be float32 [V,4] = (fx, fy, cx, cy)")
+    if w2c.dtype != torch.float32 or tuple(w2c.shape) != (v, 3, 4):
+        raise ValueError("w2c must be float32 [V,3,4] (inverse of the cam->world pose)")
+    if depth.dim() != 3 or depth.shape[0] != v or depth.dtype not in _DEPTH_CODE:
+        raise ValueError("depth must be [V,Hd,Wd] float32 (metres) or uint16 (millimetres)")
+    if fmap.dim() != 4 or fmap.shape[0] != v or fmap.dtype not in _FMAP_CODE:
+        raise ValueError("fmap must be channels-last [V,Hf,Wf,C] float32/float16/bfloat16")
+
+
+def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Tensor, fmap: torch.Tensor,
+         stride: Optional[float] = None, *, tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT,
+         views: Optional[Tuple[int, int]] = None, finalize: bool = True, plan: Optional[SuperpointPlan] = None,
+         pool: bool = False, want_maps: bool = False, accumulate_into: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+         variant: int = 0):
+    """One scale of the lifting path through ``sd3d_lift``.
+
+    Returns a dict with ``feat`` [N,C] (mean over visible views if ``finalize`` else the raw sum),
+    ``count`` [N] int32 and, on request, ``pix_idx`` / ``vis`` [V,N] and ``sp_feat`` [S,C] (``pool=True`` needs
+    ``plan``; the plan's permutation is also used as the cache-friendly processing order).
+    """
+    _check_lift_inputs(xyz, K, w2c, depth, fmap)
+    xyz, K, w2c, depth, fmap = (t.contiguous() for t in (xyz, K, w2c, depth, fmap))
+    n, v = xyz.shape[0], K.shape[0]
+    hd, wd = depth.shape[1], depth.shape[2]
+    hf, wf, c = fmap.shape[1], fmap.shape[2], fmap.shape[3]
+    if stride is None:
+        stride = wd / wf
+    vb, ve = (0, v) if views is None else (int(views[0]), int(views[1]))
+    dev = xyz.device
+    lib = _lib.load()
+    if pool and plan is None:
+        raise ValueError("pool=True needs a SuperpointPlan (sp_sort)")
+    if plan is not None and plan.n_points != n:
+        raise ValueError("plan was built for a different number of points")
+    with torch.cuda.device(dev):
+        if accumulate_into is not None:
+            feat, count = accumulate_into
+            if (feat.dtype != torch.float32 or tuple(feat.shape) != (n, c) or not feat.is_contiguous()
+                    or count.dtype != torch.int32 or count.numel() != n or not count.is_contiguous()):
+                raise ValueError("accumulate_into must be (float32 [N,C], int32 [N]) contiguous")
+        else:
+            feat = torch.empty(n, c, dtype=torch.float32, device=dev)
+            count = torch.empty(n, dtype=torch.int32, device=dev)
+        pix = vis = None
+        if want_maps:
+            pix = torch.full((v, n), -1, dtype=torch.int32, device=dev)
+            vis = torch.zeros((v, n), dtype=torch.uint8, device=dev)
+        sp_out = ws = None
+        ws_bytes = 0
+        s = 0
+        if plan is not None:
+            s = plan.n_segments
+        if pool:
+            sp_out = torch.empty(s, c, dtype=torch.float32, device=dev)
+            ws_bytes = plan.max_tasks * c * 4
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        check(lib.sd3d_lift(_ptr(xyz), n, _ptr(K), _ptr(w2c), v, vb, ve, _ptr(depth), _DEPTH_CODE[depth.dtype], hd, wd,
+                            _ptr(fmap), _FMAP_CODE[fmap.dtype], hf, wf, c, float(stride), float(tau), float(z_near),
+                            1 if accumulate_into is not None else 0, 1 if finalize else 0,
+                            _ptr(plan.perm) if plan is not None else None, _ptr(feat), _ptr(count), _ptr(pix),
+                            _ptr(vis), _ptr(plan.seg_offsets) if plan is not None else None, s,
+                            _ptr(plan.task_offsets) if plan is not None else None,
+                            _ptr(plan.task_seg) if plan is not None else None,
+                            plan.max_tasks if plan is not None else 0, plan.run if plan is not None else DEFAULT_RUN,
+                            _ptr(ws), ws_bytes, _ptr(sp_out), int(variant), _stream()), "sd3d_lift")
+    return {"feat": feat, "count": count, "pix_idx": pix, "vis": vis, "sp_feat": sp_out}
+
+
+def lift_finalize(sum_inout: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
+    """In place ``sum / max(count,1)`` (used after the multi-GPU all-reduce of (sum, count))."""
+    _need_cuda("sum", sum_inout)
+    _need_cuda("count", count)
+    if sum_inout.dtype != torch.float32 or not sum_inout.is_contiguous() or sum_inout.dim() != 2:
+        raise ValueError("sum must be contiguous float32 [N,C]")
+    if count.dtype != torch.int32 or count.numel() != sum_inout.shape[0]:
+        raise ValueError("count must be int32 [N]")
+    with torch.cuda.device(sum_inout.device):
+        check(_lib.load().sd3d_lift_finalize(_ptr(sum_inout), _ptr(count.contiguous()), sum_inout.shape[0],
+                                             sum_inout.shape[1], _stream()), "sd3d_lift_finalize")
+    return sum_inout
+
+
+def lift_features(xyz: torch.Tensor, K: torch.Tensor, pose_w2c: torch.Tensor, depth: torch.Tensor,
+                  fmaps: Sequence[torch.Tensor], *, tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT,
+                  strides: Optional[Sequence[float]] = None, order: Optional[SuperpointPlan] = None) -> List[torch.Tensor]:
+    """List over scales of ``[N,C]`` float32 tensors == the content of ``features_2d/{scene}.pth`` that the
+    reference loader reads (scannet200.py:219-224) and averages over scales (:233-234)."""
+    out = []
+    for i, fm in enumerate(fmaps):
+        s = None if strides is None else float(strides[i])
+        out.append(lift(xyz, K, pose_w2c, depth, fm, s, tau=tau, z_near=z_near, plan=order)["feat"])
+    return out
+
+
+def scale_mean(feats: Sequence[torch.Tensor]) -> torch.Tensor:
+    """``torch.stack(points_2dfeats, dim=0).mean(dim=0)`` of scannet200.py:233-234 in one pass."""
+    if len(feats) == 0:
+        raise ValueError("need at least one scale")
+    for f in feats:
+        _need_cuda("feats[i]", f)
+        if f.dtype != torch.float32 or f.shape != feats[0].shape:
+            raise ValueError("all scales must be float32 with equal shapes")
+    feats = [f.contiguous() for f in feats]
+    out = torch.empty_like(feats[0])
+    arr = (ctypes.c_void_p * len(feats))(*[f.data_ptr() for f in feats])
+    with torch.cuda.device(out.device):
+        check(_lib.load().sd3d_scale_mean(arr, len(feats), out.numel(), _ptr(out), _stream()), "sd3d_scale_mean")
+    return out
+
+
+def lift_and_pool(xyz, K, pose_w2c, depth, fmap, sp_ids: torch.Tensor, n_superpoints: Optional[int] = None, *,
+                  stride: Optional[float] = None, tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT,
+                  run: int = DEFAULT_RUN, variant: int = 0):
+    """The whole hot path for one scene: sort by superpoint -> fused lift + mean + superpoint pooling.
+    Returns (points_2dfeats [N,C], count [N], sp_feats [S,C], plan)."""
+    plan = sp_sort(sp_ids, n_superpoints, run=run)
+    r = lift(xyz, K, pose_w2c, depth, fmap, stride, tau=tau, z_near=z_near, plan=plan, pool=True, variant=variant)
+    return r["feat"], r["count"], r["sp_feat"], plan
+
+
+# ---------------------------------------------------------------------------------------------------
+# mask logits
+# ---------------------------------------------------------------------------------------------------
+def mask_logits(q: torch.Tensor, mf: torch.Tensor, precision: str = "fp32", threshold: Optional[float] = None):
+    """``torch.einsum('nd,md->nm', q, mf)`` (instance_seg_3d_decoder.py:567). ``precision='bf16'`` runs the
+    tcgen05 tensor-core kernel (bf16 operands, fp32 accumulate). With ``threshold`` also returns the fused
+    attention mask of :568-571 (bool [n,S])."""
+    _need_cuda("q", q)
+    _need_cuda("mf", mf)
+    if q.dim() != 2 or mf.dim() != 2 or q.shape[1] != mf.shape[1]:
+        raise ValueError(f"einsum 'nd,md->nm' needs [n,d] x [S,d], got {tuple(q.shape)} x {tuple(mf.shape)}")
+    if q.dtype != torch.float32 or mf.dtype != torch.float32:
+        raise Sd3dError("mask_logits takes float32 operands (the reference runs amp=False)")
+    code = {"fp32": _lib.F32, "f32": _lib.F32, "bf16": _lib.BF16}.get(precision)
+    if code is None:
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    q, mf = q.contiguous(), mf.contiguous()
+    n, d = q.shape
+    s = mf.shape[0]
+    dev = q.device
+    with torch.cuda.device(dev):
+        out = torch.empty(n, s, dtype=torch.float32, device=dev)
+        attn = torch.empty(n, s, dtype=torch.uint8, device=dev) if threshold is not None else None
+        check(_lib.load().sd3d_mask_logits(_ptr(q), _ptr(mf), n, s, d, code, _ptr(out),
+                                           float(threshold) if threshold is not None else 0.0, _ptr(attn), _stream()),
+              "sd3d_mask_logits")
+    if threshold is not None:
+        return out, attn.view(torch.bool)
+    return out

@@ -1,0 +1,107 @@
+"""Drop-in hooks with the reference's call patterns (citations relative to /root/reference).
+
+The reference modules cannot be imported here (mmengine / spconv / MinkowskiEngine / torch_scatter are
+not installed), so the hooks are written against the exact tensor contracts of their call sites:
+
+* :func:`install_torch_scatter_shim` -- makes ``from torch_scatter import scatter_mean``
+  (segdino3d/models/backbone/spconvunet.py:17, minkunet.py:16) resolve to :func:`ops.scatter_mean`.
+* :func:`batch_superpoint_ids` / :func:`pool_superpoints` -- the id-offset batching + pooling + split of
+  ``SpConvUNet.forward_wrapper`` (spconvunet.py:365-373,390-395) and ``Res16UNetBase.forward_wrapper``
+  (minkunet.py:634-650) with ONE sort shared by every pooled tensor of the batch.
+* :func:`forward_head_masks` -- the mask part of ``ScanNetQueryDecoder._forward_head``
+  (decoder/instance_seg_3d_decoder.py:567-574): logits + attention masks per scene.
+* :class:`PointFeatureLifter` -- fills ``targets[i]["extra_features"]["points_2dfeats"]``, the slot the
+  backbones read at spconvunet.py:378 / minkunet.py:612-618 (the reference loads it from disk,
+  datasets/dataset/scannet200.py:219-234).
+INTEGRATION.md shows the three-line patches a maintainer applies on the reference side.
+"""
+from __future__ import annotations
+
+import sys
+import types
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+
+def install_torch_scatter_shim(force: bool = False) -> types.ModuleType:
+    """Register a module named ``torch_scatter`` whose ``scatter_mean`` is the sm_100a kernel path."""
+    if "torch_scatter" in sys.modules and not force:
+        mod = sys.modules["torch_scatter"]
+        if getattr(mod, "__sd3d_shim__", False):
+            return mod
+        raise RuntimeError("a real torch_scatter is already imported; pass force=True to override it")
+    mod = types.ModuleType("torch_scatter")
+    mod.__sd3d_shim__ = True
+    mod.scatter_mean = ops.scatter_mean
+    sys.modules["torch_scatter"] = mod
+    return mod
+
+
+def batch_superpoint_ids(targets: Sequence[Dict]) -> Tuple[torch.Tensor, List[int]]:
+    """spconvunet.py:365-373: per-scene ids + running ``max()+1`` bias -> (hstack ids, batch_offsets)."""
+    batch_offsets = [0]
+    bias = 0
+    ids = []
+    for tgt in targets:
+        sp = tgt["extra_features"]["super_point_masks"].clone()
+        sp += bias
+        bias = int(sp.max().item()) + 1
+        batch_offsets.append(bias)
+        ids.append(sp)
+    return torch.hstack(ids), batch_offsets
+
+
+def pool_superpoints(tensors: Sequence[torch.Tensor], sp_pts_masks: torch.Tensor, batch_offsets: Sequence[int],
+                     exact: bool = True) -> List[List[torch.Tensor]]:
+    """``scatter_mean(t, sp_pts_masks, dim=0)`` for every tensor in ``tensors`` (backbone features,
+    DINO-X features, coordinates: spconvunet.py:390,392,325) sharing one sort, then the per-scene split of
+    spconvunet.py:393-395. Returns, per input tensor, the list over scenes of ``[S_i, C]``."""
+    plan = ops.sp_sort(sp_pts_masks, batch_offsets[-1])
+    out = []
+    for t in tensors:
+        pooled = ops.sp_mean(t.float().contiguous(), plan, exact=exact)
+        out.append([pooled[batch_offsets[i]: batch_offsets[i + 1]] for i in range(len(batch_offsets) - 1)])
+    return out
+
+
+def forward_head_masks(norm_queries: Sequence[torch.Tensor], mask_feats: Sequence[torch.Tensor],
+                       mask_attention_threshold: Optional[float], precision: str = "fp32"):
+    """instance_seg_3d_decoder.py:567-574 for a batch given as python lists (one entry per scene):
+    returns (pred_masks, attn_masks or None)."""
+    pred_masks, attn_masks = [], []
+    for q, mf in zip(norm_queries, mask_feats):
+        if mask_attention_threshold is not None:
+            pm, am = ops.mask_logits(q, mf, precision=precision, threshold=mask_attention_threshold)
+            attn_masks.append(am.detach())
+        else:
+            pm = ops.mask_logits(q, mf, precision=precision)
+        pred_masks.append(pm)
+    return pred_masks, (attn_masks if mask_attention_threshold is not None else None)
+
+
+class PointFeatureLifter:
+    """Pre-backbone hook: lifts DINO-X maps to per-point features on the GPU and stores them where the
+    reference expects the precomputed ones.
+
+    ``views[i]`` is a dict with ``K [V,4]``, ``w2c [V,3,4]``, ``depth [V,Hd,Wd]`` and ``fmaps`` (list over
+    scales of channels-last ``[V,Hl,Wl,C]``); ``samples[i][:, :3]`` must be the RAW world xyz
+    (augmentation moves xyz after lifting in the reference pipeline)."""
+
+    def __init__(self, tau: float = ops.TAU_DEFAULT, z_near: float = ops.Z_NEAR_DEFAULT,
+                 mode_fuse_multi_scale_2d_feats: str = "mean"):
+        if mode_fuse_multi_scale_2d_feats != "mean":
+            raise NotImplementedError(mode_fuse_multi_scale_2d_feats)  # scannet200.py:235-236
+        self.tau, self.z_near = tau, z_near
+
+    def __call__(self, samples: Sequence[torch.Tensor], targets: Sequence[Dict], views: Sequence[Dict]):
+        for pts, tgt, vw in zip(samples, targets, views):
+            xyz = pts[:, :3].contiguous()
+            sp = tgt["extra_features"].get("super_point_masks")
+            plan = ops.sp_sort(sp) if sp is not None else None
+            feats = ops.lift_features(xyz, vw["K"], vw["w2c"], vw["depth"], vw["fmaps"], tau=self.tau,
+                                      z_near=self.z_near, strides=vw.get("strides"), order=plan)
+            tgt["extra_features"]["points_2dfeats"] = feats[0] if len(feats) == 1 else ops.scale_mean(feats)
+        return targets
