@@ -49,14 +49,16 @@ int sd3d_device_sms(void);
  *   segdino3d/models/backbone/spconvunet.py:390,392 ; minkunet.py:639,641 (index = int64 ids).
  * idx[N] int64 ids in [0,S) (ids outside that range are parked after seg_offsets[S] and ignored).
  * perm[N] int32: point indices, superpoint by superpoint, ascending point index inside each.
- * seg_offsets[S+1] int32: superpoint s owns perm[seg_offsets[s] .. seg_offsets[s+1]).
+ * seg_offsets[S+2] int32: superpoint s owns perm[seg_offsets[s] .. seg_offsets[s+1]); the last pair
+ *   [seg_offsets[S], seg_offsets[S+1]=N) holds the points whose id was outside [0,S).
  * --------------------------------------------------------------------------------------------- */
 size_t sd3d_sp_sort_workspace_bytes(int64_t N, int64_t S);
 int sd3d_sp_sort(const int64_t* idx, int64_t N, int64_t S, int32_t* perm, int32_t* seg_offsets, void* ws,
                  size_t ws_bytes, void* stream);
 
 /* Splits every superpoint into runs of <= `run` consecutive sorted points (the unit one warp reduces).
- * task_offsets[S+1]: superpoint s owns tasks [task_offsets[s], task_offsets[s+1]); task_seg[t] = s.
+ * task_offsets[S+2]: superpoint s owns tasks [task_offsets[s], task_offsets[s+1]); task_seg[t] = s
+ * (segment S = the invalid-id points, which are lifted but never pooled).
  * max_tasks = sd3d_sp_max_tasks(N,S,run) is the size the caller must give task_seg. */
 int64_t sd3d_sp_max_tasks(int64_t N, int64_t S, int run);
 int sd3d_sp_tasks(const int32_t* seg_offsets, int64_t S, int run, int32_t* task_offsets, int32_t* task_seg,
@@ -90,15 +92,21 @@ int sd3d_sp_mean(const float* src, const int32_t* perm, const int32_t* seg_offse
  * order (nullable) int32[N]: processing order (perm from sd3d_sp_sort; spatially coherent order makes
  *   the gather cache-friendly). Results do not depend on it.
  * pix_idx[V,N] int32 (wi*Wd+ui or -1) and vis[V,N] u8: nullable parity outputs.
- * Fused pooling (sp_out != NULL): needs order/seg_offsets/task_offsets/task_seg/run from the plan
- *   entries above, finalize != 0, ws >= max_tasks*C*4 bytes; sp_out[S,C] = scatter_mean(out_feat, idx).
+ * Fused pooling (pool != 0): needs order/seg_offsets/task_offsets/task_seg/run from the plan entries
+ *   above, finalize != 0 and ws >= max_tasks*C*4 bytes; the kernel leaves one partial row per run in ws
+ *   and sd3d_sp_combine(ws, ...) then yields sp_out[S,C] = scatter_mean(out_feat, idx).
+ * variant: 0 = default points-per-warp group; 1/2/4/8 select the group size (tuning, C=256 fp32 maps).
  * --------------------------------------------------------------------------------------------- */
 int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin, int view_end,
               const void* depth, int depth_dtype, int Hd, int Wd, const void* fmap, int fmap_dtype, int Hf, int Wf,
               int C, float stride, float tau, float z_near, int accumulate, int finalize, const int32_t* order,
               float* out_feat, int32_t* count, int32_t* pix_idx, uint8_t* vis, const int32_t* seg_offsets,
               int64_t S, const int32_t* task_offsets, const int32_t* task_seg, int64_t max_tasks, int run, void* ws,
-              size_t ws_bytes, float* sp_out, int variant, void* stream);
+              size_t ws_bytes, int pool, int variant, void* stream);
+
+/* second half of the fused pooling: sp_out[s,:] = (sum of the run partials of s, in run order) / max(|s|,1) */
+int sd3d_sp_combine(const void* partials, const int32_t* task_offsets, const int32_t* seg_offsets, int64_t S, int C,
+                    float* sp_out, void* stream);
 
 /* feat = sum / (float)max(count,1) in place (Appendix A `feat_l`); used after the multi-GPU all-reduce */
 int sd3d_lift_finalize(float* sum_inout, const int32_t* count, int64_t N, int C, void* stream);

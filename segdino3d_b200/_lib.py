@@ -32,7 +32,8 @@ SYMBOLS = {
                           c_float, c_float, c_float, c_int, c_int,                         # stride tau z_near acc fin
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,                # order out count pix vis
                           c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,           # seg_off S task_off task_seg max_tasks run
-                          c_void_p, c_size_t, c_void_p, c_int, c_void_p]),                 # ws ws_bytes sp_out variant stream
+                          c_void_p, c_size_t, c_int, c_int, c_void_p]),                    # ws ws_bytes pool variant stream
+    "sd3d_sp_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "sd3d_lift_finalize": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "sd3d_scale_mean": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "sd3d_mask_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p,

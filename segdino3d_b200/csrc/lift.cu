@@ -360,7 +360,7 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
                          int fmap_dtype, int Hf, int Wf, int C, float stride, float tau, float z_near, int accumulate,
                          int finalize, const int32_t* order, float* out_feat, int32_t* count, int32_t* pix_idx,
                          uint8_t* vis, const int32_t* seg_offsets, int64_t S, const int32_t* task_offsets,
-                         const int32_t* task_seg, int64_t max_tasks, int run, void* ws, size_t ws_bytes, float* sp_out,
+                         const int32_t* task_seg, int64_t max_tasks, int run, void* ws, size_t ws_bytes, int pool_,
                          int variant, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (N < 0 || V < 0 || view_begin < 0 || view_end > V || view_begin > view_end || Hd <= 0 || Wd <= 0 || Hf <= 0 ||
@@ -389,20 +389,17 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
         set_error("sd3d_lift: K4/w2c/fmap/out_feat must be 16-byte aligned");
         return SD3D_ERR_ARG;
     }
-    const bool pool = sp_out != nullptr;
+    const bool pool = pool_ != 0;
     if (run <= 0) run = 32;
     if (pool) {
         if (!finalize || order == nullptr || seg_offsets == nullptr || task_offsets == nullptr ||
             task_seg == nullptr || ws == nullptr || S < 0 || max_tasks < sd3d_sp_max_tasks(N, S, run) ||
-            ws_bytes < (size_t)max_tasks * C * sizeof(float) || !aligned16(ws) || !aligned16(sp_out)) {
+            ws_bytes < (size_t)max_tasks * C * sizeof(float) || !aligned16(ws)) {
             set_error("sd3d_lift: fused pooling needs finalize=1, order, seg_offsets, task tables and ws >= max_tasks*C*4");
             return SD3D_ERR_ARG;
         }
     }
-    if (N == 0) {
-        if (pool && S > 0) cudaMemsetAsync(sp_out, 0, (size_t)S * C * sizeof(float), stream);
-        return check_launch("sd3d_lift(empty)");
-    }
+    if (N == 0) return SD3D_OK;  // task_offsets are all zero -> sd3d_sp_combine writes zero rows
     LiftParams p;
     p.xyz = xyz; p.N = N; p.K4 = K4; p.w2c = w2c; p.v_begin = view_begin; p.v_end = view_end;
     p.depth = depth; p.depth_u16 = depth_dtype == SD3D_U16; p.Hd = Hd; p.Wd = Wd;
@@ -422,12 +419,26 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
             return SD3D_ERR_UNSUPPORTED;
     }
     if (rc != SD3D_OK) return rc;
-    if (pool && S > 0) {
-        const int64_t threads = S * (int64_t)(C / 4);
-        sp_combine_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
-            p.partials, task_offsets, seg_offsets, (int32_t)S, C, sp_out);
-    }
     return check_launch("sd3d_lift");
+}
+
+extern "C" int sd3d_sp_combine(const void* partials, const int32_t* task_offsets, const int32_t* seg_offsets,
+                               int64_t S, int C, float* sp_out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (S < 0 || C <= 0 || C % 4 != 0 || S >= (int64_t(1) << 30)) {
+        set_error("sd3d_sp_combine: bad shape S=%lld C=%d (C must be a multiple of 4)", (long long)S, C);
+        return SD3D_ERR_ARG;
+    }
+    if (S == 0) return SD3D_OK;
+    if (partials == nullptr || task_offsets == nullptr || seg_offsets == nullptr || sp_out == nullptr ||
+        !aligned16(partials) || !aligned16(sp_out)) {
+        set_error("sd3d_sp_combine: null or misaligned buffer");
+        return SD3D_ERR_ARG;
+    }
+    const int64_t threads = S * (int64_t)(C / 4);
+    sp_combine_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
+        reinterpret_cast<const float*>(partials), task_offsets, seg_offsets, (int32_t)S, C, sp_out);
+    return check_launch("sd3d_sp_combine");
 }
 
 extern "C" int sd3d_lift_finalize(float* sum_inout, const int32_t* count, int64_t N, int C, void* stream_) {

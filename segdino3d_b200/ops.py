@@ -209,12 +209,13 @@ def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Ten
          stride: Optional[float] = None, *, tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT,
          views: Optional[Tuple[int, int]] = None, finalize: bool = True, plan: Optional[SuperpointPlan] = None,
          pool: bool = False, want_maps: bool = False, accumulate_into: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-         variant: int = 0):
+         variant: int = 0, events: Optional[Tuple[torch.cuda.Event, torch.cuda.Event]] = None):
     """One scale of the lifting path through ``sd3d_lift``.
 
     Returns a dict with ``feat`` [N,C] (mean over visible views if ``finalize`` else the raw sum),
     ``count`` [N] int32 and, on request, ``pix_idx`` / ``vis`` [V,N] and ``sp_feat`` [S,C] (``pool=True`` needs
     ``plan``; the plan's permutation is also used as the cache-friendly processing order).
+    ``events`` (bench only): a pair of CUDA events recorded immediately before / after the lift kernel.
     """
     _check_lift_inputs(xyz, K, w2c, depth, fmap)
     xyz, K, w2c, depth, fmap = (t.contiguous() for t in (xyz, K, w2c, depth, fmap))
@@ -252,6 +253,8 @@ def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Ten
             sp_out = torch.empty(s, c, dtype=torch.float32, device=dev)
             ws_bytes = plan.max_tasks * c * 4
             ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        if events is not None:
+            events[0].record()
         check(lib.sd3d_lift(_ptr(xyz), n, _ptr(K), _ptr(w2c), v, vb, ve, _ptr(depth), _DEPTH_CODE[depth.dtype], hd, wd,
                             _ptr(fmap), _FMAP_CODE[fmap.dtype], hf, wf, c, float(stride), float(tau), float(z_near),
                             1 if accumulate_into is not None else 0, 1 if finalize else 0,
@@ -260,7 +263,12 @@ def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Ten
                             _ptr(plan.task_offsets) if plan is not None else None,
                             _ptr(plan.task_seg) if plan is not None else None,
                             plan.max_tasks if plan is not None else 0, plan.run if plan is not None else DEFAULT_RUN,
-                            _ptr(ws), ws_bytes, _ptr(sp_out), int(variant), _stream()), "sd3d_lift")
+                            _ptr(ws), ws_bytes, 1 if pool else 0, int(variant), _stream()), "sd3d_lift")
+        if events is not None:
+            events[1].record()
+        if pool:
+            check(lib.sd3d_sp_combine(_ptr(ws), _ptr(plan.task_offsets), _ptr(plan.seg_offsets), s, c, _ptr(sp_out),
+                                      _stream()), "sd3d_sp_combine")
     return {"feat": feat, "count": count, "pix_idx": pix, "vis": vis, "sp_feat": sp_out}
 
 

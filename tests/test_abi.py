@@ -1,0 +1,82 @@
+"""CPU tests of the boundary: libsd3d.so loads, exports exactly what include/sd3d.h declares, and the
+host mirror refuses CPU tensors (no CPU fallback). No compute entry is called here."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import segdino3d_b200 as sd
+from segdino3d_b200 import _lib, plugin
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sd3d.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sd3d_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/sd3d.h but not exported"
+    assert sorted(_lib.SYMBOLS) == declared  # the Python binding covers the whole header, nothing more
+    assert lib.sd3d_version() == 100
+
+
+def test_pure_host_entries():
+    lib = _lib.load()
+    assert lib.sd3d_sp_max_tasks(100, 7, 32) == 4 + 7 + 1
+    assert lib.sd3d_sp_max_tasks(100, 7, 0) == -1
+    assert lib.sd3d_sp_sort_workspace_bytes(1000, 10) >= 4 * 1000 * 4
+
+
+def test_no_cpu_fallback():
+    x, i = torch.zeros(4, 4), torch.zeros(4, dtype=torch.long)
+    with pytest.raises(sd.Sd3dError):
+        sd.scatter_mean(x, i, dim=0)
+    with pytest.raises(sd.Sd3dError):
+        sd.mask_logits(torch.zeros(2, 64), torch.zeros(3, 64))
+    with pytest.raises(sd.Sd3dError):
+        sd.sp_sort(i)
+    with pytest.raises(sd.Sd3dError):
+        sd.lift(torch.zeros(1, 3), torch.zeros(1, 4), torch.zeros(1, 3, 4), torch.zeros(1, 4, 4), torch.zeros(1, 1, 1, 4))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "segdino3d_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "lift_ref" not in text, f
+
+
+def test_torch_scatter_shim():
+    import sys
+    had = sys.modules.pop("torch_scatter", None)
+    try:
+        mod = plugin.install_torch_scatter_shim()
+        from torch_scatter import scatter_mean
+        assert scatter_mean is sd.scatter_mean and mod.__sd3d_shim__
+        assert plugin.install_torch_scatter_shim() is mod
+    finally:
+        sys.modules.pop("torch_scatter", None)
+        if had is not None:
+            sys.modules["torch_scatter"] = had
+
+
+def test_batch_superpoint_ids_matches_reference_pattern():
+    from oracle import scatter_oracle as so
+    sps = [torch.tensor([0, 2, 2, 1]), torch.tensor([1, 0]), torch.tensor([3, 3])]
+    targets = [{"extra_features": {"super_point_masks": s}} for s in sps]
+    ids, offs = plugin.batch_superpoint_ids(targets)
+    ids2, offs2 = so.batch_superpoint_ids_oracle(sps)
+    assert torch.equal(ids, ids2) and offs == offs2
+    assert sps[0].tolist() == [0, 2, 2, 1]  # inputs are cloned, not mutated (spconvunet.py:369)

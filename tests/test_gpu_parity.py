@@ -1,0 +1,364 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libsd3d.so) against the CPU oracle on identical
+seeded inputs. Integer outputs (pix_idx, vis, count, perm, seg_offsets) must be bit-exact; fp32 features
+are bit-exact in the exact modes and within 1e-5 (relative to the row norm) in the run-partial mode; the
+bf16 tensor-core mask logits within 1e-2."""
+import numpy as np
+import pytest
+import torch
+
+import segdino3d_b200 as sd
+from oracle import c_ref
+from oracle import lift_oracle as lo
+from oracle import mask_oracle as mo
+from oracle import scatter_oracle as so
+from segdino3d_b200 import plugin
+from segdino3d_b200.synth import make_decoder_operands, make_scene
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def rel_row_err(got: torch.Tensor, want: torch.Tensor) -> float:
+    """max over rows of |got-want|_inf / max(|want row|_inf, tiny): the 1e-5 criterion of the north star."""
+    got, want = got.double().cpu(), want.double().cpu()
+    if want.numel() == 0:
+        return 0.0
+    scale = want.abs().amax(dim=-1, keepdim=True).clamp(min=1e-6)
+    return float(((got - want).abs() / scale).max())
+
+
+# ----------------------------------------------------------------------------------------------------
+# sp_sort / sp_mean / scatter_mean
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,s", [(0, 5), (1, 1), (37, 3), (1000, 1), (5000, 500), (100_000, 521), (70_000, 5000),
+                                 (3000, 1023), (3000, 1024), (20_000, 70_000), (300_000, 2_000_000)])
+def test_sp_sort_bit_exact(n, s):
+    g = torch.Generator().manual_seed(n + s)
+    idx = torch.randint(0, s, (n,), generator=g)
+    plan = sd.sp_sort(idx.to(DEV), s)
+    perm, offs = so.sp_sort_oracle(idx, s)
+    assert torch.equal(plan.perm.cpu(), perm)
+    assert torch.equal(plan.seg_offsets[: s + 1].cpu(), offs)
+    assert plan.seg_offsets[s + 1].item() == n
+    # run table: every superpoint is tiled by runs of <= run points
+    t_off = plan.task_offsets.cpu()
+    sizes = (offs[1:] - offs[:-1]).long()
+    want_tasks = (sizes + plan.run - 1) // plan.run
+    assert torch.equal((t_off[1: s + 1] - t_off[:s]).long(), want_tasks)
+    n_tasks = int(t_off[s + 1])
+    assert n_tasks <= plan.max_tasks
+    seg_of_task = plan.task_seg.cpu()[:n_tasks].long()
+    assert torch.equal(seg_of_task, torch.repeat_interleave(torch.arange(s + 1), torch.cat([want_tasks, t_off[s + 1:s + 2].long() - t_off[s:s + 1].long()])))
+
+
+def test_sp_sort_invalid_ids_are_parked():
+    idx = torch.tensor([3, -1, 0, 99, 3, 0, 5, 2])
+    plan = sd.sp_sort(idx.to(DEV), 5)
+    assert plan.perm.cpu().tolist() == [2, 5, 7, 0, 4, 1, 3, 6]  # valid ids sorted stably, then ids outside [0,5)
+    assert plan.seg_offsets.cpu().tolist() == [0, 2, 2, 3, 5, 5, 8]
+
+
+def test_sp_sort_default_segments_is_max_plus_one():
+    idx = torch.tensor([4, 0, 4, 0, 0, 7], device=DEV)
+    plan = sd.sp_sort(idx)
+    assert plan.n_segments == 8
+
+
+@pytest.mark.parametrize("c", [1, 3, 32, 96, 130, 256, 512])
+@pytest.mark.parametrize("n,s", [(5000, 60), (100_000, 521)])
+def test_sp_mean_exact_is_bit_identical_to_cpu_reference(n, s, c):
+    g = torch.Generator().manual_seed(c * 7 + n)
+    src = torch.randn(n, c, generator=g) * 3 + 0.5
+    idx = torch.randint(0, s, (n,), generator=g)
+    idx[idx == 7] = 8  # an empty id in the middle
+    want = so.scatter_mean_oracle(src, idx, dim=0, dim_size=s)
+    got = sd.scatter_mean(src.to(DEV), idx.to(DEV), dim=0, dim_size=s)
+    assert got.shape == want.shape and got.dtype == torch.float32
+    assert torch.equal(got.cpu(), want)
+    assert got[7].abs().sum().item() == 0.0
+    fast = sd.scatter_mean(src.to(DEV), idx.to(DEV), dim=0, dim_size=s, exact=False)
+    assert rel_row_err(fast, want) <= 1e-5
+    # deterministic: same bits on a second run
+    assert torch.equal(fast, sd.scatter_mean(src.to(DEV), idx.to(DEV), dim=0, dim_size=s, exact=False))
+
+
+def test_scatter_mean_signature_variants():
+    g = torch.Generator().manual_seed(1)
+    src = torch.randn(400, 5, generator=g)
+    idx = torch.randint(0, 9, (400,), generator=g)
+    want = so.scatter_mean_oracle(src, idx, dim=0)
+    a = sd.scatter_mean(src.to(DEV), idx.to(DEV), 0)
+    b = sd.scatter_mean(src.to(DEV), idx.to(DEV), dim=-2)
+    assert torch.equal(a.cpu(), want) and torch.equal(b.cpu(), want)
+    one_d = sd.scatter_mean(src[:, 0].contiguous().to(DEV), idx.to(DEV), dim=0)
+    assert torch.equal(one_d.cpu(), so.scatter_mean_oracle(src[:, 0].contiguous(), idx, dim=0))
+    with pytest.raises(sd.Sd3dError):
+        sd.scatter_mean(src.to(DEV), idx.to(DEV)[:5].repeat(80), dim=1)
+    empty = sd.scatter_mean(src[:0].to(DEV), idx[:0].to(DEV), dim=0)
+    assert empty.shape == (0, 5)
+    # adversarial: one superpoint with half of all points, gaps in the id space
+    sc = make_scene(n_points=20_000, n_views=1, hd=24, wd=32, stride=8, channels=4, seed=3, adversarial_sp=True)
+    src = torch.randn(20_000, 96, generator=g)
+    want = so.scatter_mean_oracle(src, sc.sp_ids, dim=0)
+    assert torch.equal(sd.scatter_mean(src.to(DEV), sc.sp_ids.to(DEV), dim=0).cpu(), want)
+    assert rel_row_err(sd.scatter_mean(src.to(DEV), sc.sp_ids.to(DEV), dim=0, exact=False), want) <= 1e-5
+
+
+def test_backbone_pooling_call_pattern():
+    """The id-offset batching + pooling + split of SpConvUNet.forward_wrapper (spconvunet.py:365-395)."""
+    g = torch.Generator().manual_seed(5)
+    sizes, sps = [3000, 1200, 2500], [40, 11, 33]
+    targets, feats, dinox, coords = [], [], [], []
+    for n, s in zip(sizes, sps):
+        sp = torch.randint(0, s, (n,), generator=g)
+        sp[0] = s - 1
+        targets.append({"extra_features": {"super_point_masks": sp.to(DEV)}})
+        feats.append(torch.randn(n, 32, generator=g))
+        dinox.append(torch.randn(n, 256, generator=g))
+        coords.append(torch.randn(n, 3, generator=g))
+    ids, offs = plugin.batch_superpoint_ids(targets)
+    ids_o, offs_o = so.batch_superpoint_ids_oracle([t["extra_features"]["super_point_masks"].cpu() for t in targets])
+    assert torch.equal(ids.cpu(), ids_o) and offs == offs_o
+    pooled = plugin.pool_superpoints([torch.cat(feats).to(DEV), torch.cat(dinox).to(DEV), torch.cat(coords).to(DEV)],
+                                     ids, offs)
+    for tensors, got in zip((feats, dinox, coords), pooled):
+        want = so.scatter_mean_oracle(torch.cat(tensors), ids_o, dim=0)
+        for i in range(3):
+            assert torch.equal(got[i].cpu(), want[offs_o[i]: offs_o[i + 1]])
+
+
+# ----------------------------------------------------------------------------------------------------
+# lifting
+# ----------------------------------------------------------------------------------------------------
+def _to_dev(sc):
+    return sc.to(DEV)
+
+
+def _check_lift(sc, depth=None, variant=0, fmap=None):
+    depth = sc.depth if depth is None else depth
+    fmap = sc.fmap if fmap is None else fmap
+    a, c, p, v = lo.lift_accumulate_oracle(sc.xyz, sc.K, sc.w2c, depth, fmap, sc.stride)
+    r = sd.lift(sc.xyz.to(DEV), sc.K.to(DEV), sc.w2c.to(DEV), depth.to(DEV), fmap.to(DEV), sc.stride, finalize=False,
+                want_maps=True, variant=variant)
+    assert torch.equal(r["count"].cpu(), c), "count"
+    assert torch.equal(r["vis"].cpu(), v), "vis"
+    assert torch.equal(r["pix_idx"].cpu(), p), "pix_idx"
+    assert torch.equal(r["feat"].cpu(), a), f"sum differs: rel {rel_row_err(r['feat'], a):.3e}"
+    f = sd.lift(sc.xyz.to(DEV), sc.K.to(DEV), sc.w2c.to(DEV), depth.to(DEV), fmap.to(DEV), sc.stride, variant=variant)
+    assert torch.equal(f["feat"].cpu(), lo.lift_finalize_oracle(a, c)), "mean"
+    assert f["pix_idx"] is None
+    return a, c, p, v
+
+
+def test_lift_golden_fixture(golden):
+    g = {k: torch.from_numpy(v) for k, v in golden.items()}
+    r = sd.lift(g["xyz"].to(DEV), g["K"].to(DEV), g["w2c"].to(DEV), g["depth"].to(DEV), g["fmap"].to(DEV),
+                float(g["stride"]), finalize=False, want_maps=True)
+    assert torch.equal(r["count"].cpu(), g["count"]) and torch.equal(r["vis"].cpu(), g["vis"])
+    assert torch.equal(r["pix_idx"].cpu(), g["pix_idx"]) and torch.equal(r["feat"].cpu(), g["sum"])
+    feat, cnt, sp, plan = sd.lift_and_pool(g["xyz"].to(DEV), g["K"].to(DEV), g["w2c"].to(DEV), g["depth"].to(DEV),
+                                           g["fmap"].to(DEV), g["sp_ids"].to(DEV))
+    assert torch.equal(feat.cpu(), g["feat"]) and torch.equal(cnt.cpu(), g["count"])
+    assert torch.equal(plan.perm.cpu(), g["perm"])
+    assert rel_row_err(sp, g["sp_feat"]) <= 1e-5
+    logits = sd.mask_logits(g["q"].to(DEV), g["mf"].to(DEV))
+    assert rel_row_err(logits, g["logits"]) <= 1e-5
+
+
+@pytest.mark.parametrize("channels", [4, 64, 128, 256, 384, 512, 1024])
+def test_lift_channel_widths(channels):
+    sc = make_scene(n_points=3000, n_views=7, hd=60, wd=80, stride=4, channels=channels, seed=channels, sp_target=30)
+    _check_lift(sc)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 4, 8])
+def test_lift_group_variants(small_scene, variant):
+    sc = make_scene(n_points=5000, n_views=40, hd=120, wd=160, stride=8, channels=256, seed=21, sp_target=50)
+    _check_lift(sc, variant=variant)
+
+
+@pytest.mark.parametrize("fmap_dtype", [torch.float16, torch.bfloat16])
+def test_lift_16bit_maps(fmap_dtype):
+    sc = make_scene(n_points=4000, n_views=9, hd=60, wd=80, stride=4, channels=256, seed=6, sp_target=30,
+                    fmap_dtype=fmap_dtype)
+    _check_lift(sc)
+
+
+def test_lift_u16_depth_and_many_views():
+    sc = make_scene(n_points=2500, n_views=70, hd=60, wd=80, stride=4, channels=32, seed=12, sp_target=30)
+    _check_lift(sc, depth=sc.depth_u16())
+    _check_lift(sc)
+
+
+def test_lift_edge_cases():
+    sc = make_scene(n_points=700, n_views=3, hd=48, wd=64, stride=8, channels=8, seed=9, sp_target=10)
+    d = {k: getattr(sc, k).to(DEV) for k in ("xyz", "K", "w2c", "depth", "fmap")}
+    # no points
+    r = sd.lift(d["xyz"][:0], d["K"], d["w2c"], d["depth"], d["fmap"], sc.stride)
+    assert r["feat"].shape == (0, 8) and r["count"].numel() == 0
+    # no views: every point unseen -> zero rows, count 0
+    r = sd.lift(d["xyz"], d["K"][:0], d["w2c"][:0], d["depth"][:0], d["fmap"][:0], sc.stride)
+    assert r["count"].sum().item() == 0 and r["feat"].abs().sum().item() == 0
+    # all-invisible (depth invalid everywhere)
+    r = sd.lift(d["xyz"], d["K"], d["w2c"], torch.zeros_like(d["depth"]), d["fmap"], sc.stride, want_maps=True)
+    assert r["count"].sum().item() == 0 and (r["pix_idx"] == -1).all() and r["feat"].abs().sum().item() == 0
+    # points exactly on pixel-boundary neighbourhoods: nudge u by +-1 ulp around x.5
+    base = torch.tensor([[0.0, 0.0, 2.0]])
+    K = torch.tensor([[100.0, 100.0, 50.0, 40.0]])
+    w2c = torch.eye(4)[:3][None].contiguous()
+    xs = torch.linspace(-1.2, 1.2, 4001)
+    xyz = torch.stack([xs, 0.3 * xs, torch.full_like(xs, 2.0)], 1).contiguous()
+    depth = torch.full((1, 80, 100), 2.0)
+    fmap = torch.randn(1, 20, 25, 8)
+    a, c, p, v = lo.lift_accumulate_oracle(xyz, K, w2c, depth, fmap, 4.0)
+    r = sd.lift(xyz.to(DEV), K.to(DEV), w2c.to(DEV), depth.to(DEV), fmap.to(DEV), 4.0, finalize=False, want_maps=True)
+    assert torch.equal(r["pix_idx"].cpu(), p) and torch.equal(r["count"].cpu(), c) and torch.equal(r["feat"].cpu(), a)
+    assert 0 < int(c.sum()) < 4001  # some in, some out of the frustum
+
+
+def test_lift_view_ranges_chain_bit_exactly(small_scene):
+    sc = small_scene
+    d = {k: getattr(sc, k).to(DEV) for k in ("xyz", "K", "w2c", "depth", "fmap")}
+    full = sd.lift(d["xyz"], d["K"], d["w2c"], d["depth"], d["fmap"], sc.stride, finalize=False)
+    part = sd.lift(d["xyz"], d["K"], d["w2c"], d["depth"], d["fmap"], sc.stride, finalize=False, views=(0, 4))
+    a0, c0, _, _ = lo.lift_accumulate_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride, views=range(0, 4))
+    assert torch.equal(part["feat"].cpu(), a0) and torch.equal(part["count"].cpu(), c0)
+    chained = sd.lift(d["xyz"], d["K"], d["w2c"], d["depth"], d["fmap"], sc.stride, finalize=False, views=(4, 9),
+                      accumulate_into=(part["feat"], part["count"]))
+    assert torch.equal(chained["feat"], full["feat"]) and torch.equal(chained["count"], full["count"])
+    sd.lift_finalize(chained["feat"], chained["count"])
+    a, c, _, _ = lo.lift_accumulate_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride)
+    assert torch.equal(chained["feat"].cpu(), lo.lift_finalize_oracle(a, c))
+
+
+def test_lift_order_does_not_change_results(small_scene):
+    sc = small_scene
+    d = {k: getattr(sc, k).to(DEV) for k in ("xyz", "K", "w2c", "depth", "fmap")}
+    plain = sd.lift(d["xyz"], d["K"], d["w2c"], d["depth"], d["fmap"], sc.stride)
+    plan = sd.sp_sort(sc.sp_ids.to(DEV))
+    ordered = sd.lift(d["xyz"], d["K"], d["w2c"], d["depth"], d["fmap"], sc.stride, plan=plan)
+    assert torch.equal(plain["feat"], ordered["feat"]) and torch.equal(plain["count"], ordered["count"])
+
+
+def test_multi_scale_features_and_scale_mean(small_scene):
+    sc = small_scene
+    fm2 = torch.randn(sc.K.shape[0], sc.depth.shape[1] // 8, sc.depth.shape[2] // 8, 64,
+                      generator=torch.Generator().manual_seed(2))
+    want = lo.lift_features_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, [sc.fmap, fm2])
+    got = sd.lift_features(sc.xyz.to(DEV), sc.K.to(DEV), sc.w2c.to(DEV), sc.depth.to(DEV), [sc.fmap.to(DEV), fm2.to(DEV)])
+    assert len(got) == 2 and all(torch.equal(g.cpu(), w) for g, w in zip(got, want))
+    assert torch.allclose(sd.scale_mean(got).cpu(), lo.scale_mean_oracle(want), rtol=1e-6, atol=1e-7)
+    # the pre-backbone hook fills extra_features["points_2dfeats"] (spconvunet.py:378)
+    tgt = [{"extra_features": {"super_point_masks": sc.sp_ids.to(DEV)}}]
+    pts = torch.cat([sc.xyz, torch.zeros(sc.xyz.shape[0], 3)], 1).to(DEV)
+    views = [{"K": sc.K.to(DEV), "w2c": sc.w2c.to(DEV), "depth": sc.depth.to(DEV), "fmaps": [sc.fmap.to(DEV), fm2.to(DEV)]}]
+    plugin.PointFeatureLifter()([pts], tgt, views)
+    assert torch.allclose(tgt[0]["extra_features"]["points_2dfeats"].cpu(), lo.scale_mean_oracle(want), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("adversarial", [False, True])
+def test_fused_lift_pool(adversarial):
+    sc = make_scene(n_points=30_000, n_views=12, hd=120, wd=160, stride=8, channels=256, seed=14, sp_target=150,
+                    adversarial_sp=adversarial)
+    a, c, _, _ = c_ref.lift_ref(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride, want_maps=False)
+    feat_o = lo.lift_finalize_oracle(a, c)
+    sp_o = so.scatter_mean_oracle(feat_o, sc.sp_ids, dim=0)
+    feat, cnt, sp, plan = sd.lift_and_pool(sc.xyz.to(DEV), sc.K.to(DEV), sc.w2c.to(DEV), sc.depth.to(DEV),
+                                           sc.fmap.to(DEV), sc.sp_ids.to(DEV))
+    assert torch.equal(cnt.cpu(), c) and torch.equal(feat.cpu(), feat_o)
+    assert sp.shape == sp_o.shape and rel_row_err(sp, sp_o) <= 1e-5
+    # unfused exact pooling of the lifted features is bit-identical to the CPU reference order
+    assert torch.equal(sd.sp_mean(feat, plan, exact=True).cpu(), sp_o)
+    # the multi-GPU tail: raw sums + counts -> fused finalize inside the pooling kernel
+    raw = sd.lift(sc.xyz.to(DEV), sc.K.to(DEV), sc.w2c.to(DEV), sc.depth.to(DEV), sc.fmap.to(DEV), sc.stride,
+                  finalize=False)
+    assert torch.equal(sd.sp_mean(raw["feat"], plan, exact=True, point_count=raw["count"]).cpu(), sp_o)
+    assert rel_row_err(sd.sp_mean(raw["feat"], plan, exact=False, point_count=raw["count"]), sp_o) <= 1e-5
+
+
+def test_full_size_scene_cfg2():
+    """BASELINE configs[1]: 100k points, 40 views 640x480, 256-d stride-8 maps, ~500 superpoints."""
+    sc = make_scene(seed=1235)
+    a, c, p, v = c_ref.lift_ref(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride)
+    feat_o = c_ref.finalize_ref(a, c)
+    sp_o = so.scatter_mean_oracle(feat_o, sc.sp_ids, dim=0)
+    d = sc.to(DEV)
+    feat, cnt, sp, plan = sd.lift_and_pool(d.xyz, d.K, d.w2c, d.depth, d.fmap, d.sp_ids)
+    assert torch.equal(cnt.cpu(), c)
+    assert torch.equal(feat.cpu(), feat_o)
+    assert rel_row_err(sp, sp_o) <= 1e-5
+    maps = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, want_maps=True, plan=plan)
+    assert torch.equal(maps["pix_idx"].cpu(), p) and torch.equal(maps["vis"].cpu(), v)
+    # size-independent properties: determinism, count = column sums of vis, linearity in the feature maps
+    feat2, cnt2, sp2, _ = sd.lift_and_pool(d.xyz, d.K, d.w2c, d.depth, d.fmap, d.sp_ids)
+    assert torch.equal(feat, feat2) and torch.equal(sp, sp2) and torch.equal(cnt, cnt2)
+    assert torch.equal(maps["vis"].sum(0, dtype=torch.int32), cnt)
+    doubled = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap * 2, sc.stride, plan=plan)["feat"]
+    assert torch.equal(doubled, feat * 2)  # scaling by 2 is exact in fp32
+    ones = sd.lift(d.xyz, d.K, d.w2c, d.depth, torch.ones_like(d.fmap[..., :4]).contiguous(), sc.stride)["feat"]
+    seen = cnt > 0
+    assert float(ones.max()) <= 1.0 + 1e-6  # bilinear weights are a partition of unity (< 1 only at map borders)
+    assert float(((ones[seen] - 1).abs() < 1e-6).float().mean()) > 0.97
+    assert float(ones[~seen].abs().sum()) == 0.0
+
+
+# ----------------------------------------------------------------------------------------------------
+# mask logits
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,s,d", [(200, 500, 256), (1, 1, 64), (37, 65, 128), (500, 500, 256), (129, 513, 192),
+                                   (200, 500, 100)])
+def test_mask_logits_fp32(n, s, d):
+    q, mf = make_decoder_operands(n, s, d, seed=n + s)
+    want64 = mo.mask_logits_f64(q, mf)
+    got = sd.mask_logits(q.to(DEV), mf.to(DEV), precision="fp32")
+    scale = float(q.norm(dim=1).max() * mf.norm(dim=1).max())
+    assert float((got.double().cpu() - want64).abs().max()) <= 1e-5 * scale
+    assert float((got.cpu() - mo.mask_logits_oracle(q, mf)).abs().max()) <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("n,s,d", [(200, 500, 256), (1, 1, 64), (37, 65, 128), (500, 500, 256), (129, 513, 192),
+                                   (300, 700, 512)])
+def test_mask_logits_tcgen05_bf16(n, s, d):
+    q, mf = make_decoder_operands(n, s, d, seed=n + s + 1)
+    got = sd.mask_logits(q.to(DEV), mf.to(DEV), precision="bf16").cpu()
+    # exact reference of what the tensor core computes: bf16-rounded operands, wide accumulation
+    want_bf = mo.mask_logits_f64(q.bfloat16().float(), mf.bfloat16().float())
+    scale = float(q.norm(dim=1).max() * mf.norm(dim=1).max())
+    assert float((got.double() - want_bf).abs().max()) <= 1e-5 * scale
+    # the north-star tolerance against the fp32 reference einsum
+    assert float((got - mo.mask_logits_oracle(q, mf)).abs().max()) <= 1e-2 * scale
+
+
+def test_mask_logits_unsupported_shapes_raise():
+    q, mf = make_decoder_operands(8, 8, 100)
+    with pytest.raises(sd.Sd3dError):
+        sd.mask_logits(q.to(DEV), mf.to(DEV), precision="bf16")  # d % 64 != 0 -> no silent fallback
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_forward_head_masks(precision):
+    """_forward_head's mask branch (instance_seg_3d_decoder.py:567-574) on a 2-scene batch."""
+    qs, mfs = [], []
+    for i, (n, s) in enumerate([(200, 500), (150, 321)]):
+        q, mf = make_decoder_operands(n, s, 256, seed=40 + i)
+        q[3] = -q[3].abs() * 0  # a zero query -> logits 0 -> sigmoid 0.5, never < 0.5
+        mf = mf * 4
+        qs.append(q)
+        mfs.append(mf)
+    pred, attn = plugin.forward_head_masks([q.to(DEV) for q in qs], [m.to(DEV) for m in mfs], 0.5, precision=precision)
+    for q, mf, pm, am in zip(qs, mfs, pred, attn):
+        want = mo.mask_logits_oracle(q, mf)
+        want_am = mo.attn_mask_oracle(want.clone(), 0.5)
+        assert am.dtype == torch.bool and am.shape == want.shape
+        tol = (1e-5 if precision == "fp32" else 1e-2) * float(q.norm(dim=1).max() * mf.norm(dim=1).max())
+        assert float((pm.cpu() - want).abs().max()) <= tol
+        decided = (want.abs() > 2 * tol)  # away from the threshold the boolean must agree exactly
+        assert float(decided.float().mean()) > 0.5 and not bool(want_am.all(1).any())
+        assert bool((am.cpu()[decided] == want_am[decided]).all())
+    # an all-masked row is reset to all-False
+    q = -torch.ones(4, 64)
+    mf = torch.ones(9, 64)
+    _, am = sd.mask_logits(q.to(DEV), mf.to(DEV), precision=precision, threshold=0.5)
+    assert not am.any()
+    pred2, attn2 = plugin.forward_head_masks([qs[0].to(DEV)], [mfs[0].to(DEV)], None, precision=precision)
+    assert attn2 is None and torch.equal(pred2[0], pred[0])
