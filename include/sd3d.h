@@ -93,10 +93,13 @@ int sd3d_sp_mean(const float* src, const int32_t* perm, const int32_t* seg_offse
  *   the gather cache-friendly). Results do not depend on it.
  * pix_idx[V,N] int32 (wi*Wd+ui or -1) and vis[V,N] u8: nullable parity outputs.
  * Fused pooling (pool != 0): needs order/seg_offsets/task_offsets/task_seg/run from the plan entries
- *   above, finalize != 0 and ws >= max_tasks*C*4 bytes; the kernel leaves one partial row per run in ws
+ *   above and finalize != 0; the kernel leaves one partial row per run at the start of ws
  *   and sd3d_sp_combine(ws, ...) then yields sp_out[S,C] = scatter_mean(out_feat, idx).
- * variant: 0 = default points-per-warp group; 1/2/4/8 select the group size (tuning, C=256 fp32 maps).
+ * ws: sd3d_lift_workspace_bytes(N, view_end-view_begin, C, pool ? max_tasks : 0) bytes: the per-point view
+ *   bit-masks written by the projection kernel (+ the run partials when pool != 0, at offset 0).
+ * variant: bit 0 = contract the bilinear blend into FFMA (not bit-exact to Appendix A, <= 1e-6 rel.).
  * --------------------------------------------------------------------------------------------- */
+size_t sd3d_lift_workspace_bytes(int64_t N, int n_views, int C, int64_t max_tasks);
 int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin, int view_end,
               const void* depth, int depth_dtype, int Hd, int Wd, const void* fmap, int fmap_dtype, int Hf, int Wf,
               int C, float stride, float tau, float z_near, int accumulate, int finalize, const int32_t* order,

@@ -26,6 +26,7 @@ SYMBOLS = {
     "sd3d_sp_tasks": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "sd3d_sp_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p,
                              c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "sd3d_lift_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int64]),
     "sd3d_lift": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,      # xyz N K4 w2c V vb ve
                           c_void_p, c_int, c_int, c_int,                                   # depth dtype Hd Wd
                           c_void_p, c_int, c_int, c_int, c_int,                            # fmap dtype Hf Wf C

@@ -73,53 +73,146 @@ __device__ __forceinline__ float4 load_tap<__nv_bfloat16>(const __nv_bfloat16* p
 }
 
 // f = ((w00*t00 + w01*t01) + w10*t10) + w11*t11 ; acc = acc + f      (Appendix A, unfused)
+template <bool FAST>
 __device__ __forceinline__ float blend1(float acc, float w00, float w01, float w10, float w11, float t00, float t01,
                                         float t10, float t11) {
+    if (FAST) {  // contracted: 4 FFMA, differs from the spec order by O(1 ulp) per sample
+        return fmaf(w11, t11, fmaf(w10, t10, fmaf(w01, t01, fmaf(w00, t00, acc))));
+    }
     float f = __fadd_rn(__fmul_rn(w00, t00), __fmul_rn(w01, t01));
     f = __fadd_rn(f, __fmul_rn(w10, t10));
     f = __fadd_rn(f, __fmul_rn(w11, t11));
     return __fadd_rn(acc, f);
 }
 
+// One bilinear sample in flight: the four tap rows (this lane's channel vectors) + the weights.
+template <int NV>
+struct Sample {
+    float w00, w01, w10, w11;
+    float4 t00[NV], t01[NV], t10[NV], t11[NV];
+};
+
+// issue the 4*NV 128-bit loads of one sample (no use of the data here -> they stay in flight)
 template <int NV, typename FT>
-__device__ __forceinline__ void gather_sample(float4 (&acc)[NV], const FT* __restrict__ fmap_v, float u, float w,
-                                              float stride, int Hf, int Wf, int C, int lane) {
+__device__ __forceinline__ void sample_issue(Sample<NV>& s, const FT* __restrict__ fmap_v, float u, float w,
+                                             float stride, int Hf, int Wf, int C, int lane) {
     const float uf = __fsub_rn(__fdiv_rn(__fadd_rn(u, 0.5f), stride), 0.5f);
     const float wf = __fsub_rn(__fdiv_rn(__fadd_rn(w, 0.5f), stride), 0.5f);
     const float x0f = floorf(uf), y0f = floorf(wf);
     const float ax = __fsub_rn(uf, x0f), ay = __fsub_rn(wf, y0f);
     const int x0 = (int)x0f, y0 = (int)y0f;
     const float omx = __fsub_rn(1.0f, ax), omy = __fsub_rn(1.0f, ay);
-    const float w00 = __fmul_rn(omx, omy), w01 = __fmul_rn(ax, omy);
-    const float w10 = __fmul_rn(omx, ay), w11 = __fmul_rn(ax, ay);
+    s.w00 = __fmul_rn(omx, omy);
+    s.w01 = __fmul_rn(ax, omy);
+    s.w10 = __fmul_rn(omx, ay);
+    s.w11 = __fmul_rn(ax, ay);
     const bool okx0 = (x0 >= 0) && (x0 < Wf), okx1 = (x0 + 1 >= 0) && (x0 + 1 < Wf);
     const bool oky0 = (y0 >= 0) && (y0 < Hf), oky1 = (y0 + 1 >= 0) && (y0 + 1 < Hf);
     const bool ok00 = oky0 && okx0, ok01 = oky0 && okx1, ok10 = oky1 && okx0, ok11 = oky1 && okx1;
     const int64_t o00 = ((int64_t)y0 * Wf + x0) * C;
     const int64_t o01 = o00 + C, o10 = o00 + (int64_t)Wf * C, o11 = o10 + C;
-    float4 t00[NV], t01[NV], t10[NV], t11[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         const int c = (k * 32 + lane) * 4;
         const bool cok = c < C;
-        t00[k] = (cok && ok00) ? load_tap<FT>(fmap_v + o00 + c) : f4_zero();
-        t01[k] = (cok && ok01) ? load_tap<FT>(fmap_v + o01 + c) : f4_zero();
-        t10[k] = (cok && ok10) ? load_tap<FT>(fmap_v + o10 + c) : f4_zero();
-        t11[k] = (cok && ok11) ? load_tap<FT>(fmap_v + o11 + c) : f4_zero();
-    }
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        acc[k].x = blend1(acc[k].x, w00, w01, w10, w11, t00[k].x, t01[k].x, t10[k].x, t11[k].x);
-        acc[k].y = blend1(acc[k].y, w00, w01, w10, w11, t00[k].y, t01[k].y, t10[k].y, t11[k].y);
-        acc[k].z = blend1(acc[k].z, w00, w01, w10, w11, t00[k].z, t01[k].z, t10[k].z, t11[k].z);
-        acc[k].w = blend1(acc[k].w, w00, w01, w10, w11, t00[k].w, t01[k].w, t10[k].w, t11[k].w);
+        s.t00[k] = (cok && ok00) ? load_tap<FT>(fmap_v + o00 + c) : f4_zero();
+        s.t01[k] = (cok && ok01) ? load_tap<FT>(fmap_v + o01 + c) : f4_zero();
+        s.t10[k] = (cok && ok10) ? load_tap<FT>(fmap_v + o10 + c) : f4_zero();
+        s.t11[k] = (cok && ok11) ? load_tap<FT>(fmap_v + o11 + c) : f4_zero();
     }
 }
 
-template <int NV, typename FT, int G>
-__global__ void __launch_bounds__(kLiftThreads) lift_kernel(const LiftParams p) {
+template <int NV, bool FAST>
+__device__ __forceinline__ void sample_accum(float4 (&acc)[NV], const Sample<NV>& s) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        acc[k].x = blend1<FAST>(acc[k].x, s.w00, s.w01, s.w10, s.w11, s.t00[k].x, s.t01[k].x, s.t10[k].x, s.t11[k].x);
+        acc[k].y = blend1<FAST>(acc[k].y, s.w00, s.w01, s.w10, s.w11, s.t00[k].y, s.t01[k].y, s.t10[k].y, s.t11[k].y);
+        acc[k].z = blend1<FAST>(acc[k].z, s.w00, s.w01, s.w10, s.w11, s.t00[k].z, s.t01[k].z, s.t10[k].z, s.t11[k].z);
+        acc[k].w = blend1<FAST>(acc[k].w, s.w00, s.w01, s.w10, s.w11, s.t00[k].w, s.t01[k].w, s.t10[k].w, s.t11[k].w);
+    }
+}
+
+// Appendix A lines `xc = ...` .. `w = ...` for one (point, view): returns zc, writes u / w
+__device__ __forceinline__ float project_point(const float4 k4, const float4 r0, const float4 r1, const float4 r2,
+                                               float px, float py, float pz, float z_near, float& u, float& w) {
+    const float xc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, px), __fmul_rn(r0.y, py)), __fmul_rn(r0.z, pz)), r0.w);
+    const float yc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, px), __fmul_rn(r1.y, py)), __fmul_rn(r1.z, pz)), r1.w);
+    const float zc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, px), __fmul_rn(r2.y, py)), __fmul_rn(r2.z, pz)), r2.w);
+    u = 0.f;
+    w = 0.f;
+    if (zc > z_near) {
+        u = __fadd_rn(__fdiv_rn(__fmul_rn(k4.x, xc), zc), k4.z);
+        w = __fadd_rn(__fdiv_rn(__fmul_rn(k4.y, yc), zc), k4.w);
+    }
+    return zc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: projection + depth-visibility (step a-1). One warp per point, LANE = VIEW within a 32-view chunk;
+// __ballot_sync packs the predicate into one mask word per (point, chunk). Integer outputs only.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kProjThreads = 256;
+constexpr int kProjWarps = kProjThreads / 32;
+
+__global__ void __launch_bounds__(kProjThreads) project_kernel(const LiftParams p, uint32_t* __restrict__ masks,
+                                                               int nchunks) {
     const int lane = lane_id();
-    const int64_t task = (int64_t)blockIdx.x * kLiftWarps + (threadIdx.x >> 5);
+    const int64_t pid = (int64_t)blockIdx.x * kProjWarps + (threadIdx.x >> 5);
+    if (pid >= p.N) return;
+    const float px = __ldg(p.xyz + 3 * pid), py = __ldg(p.xyz + 3 * pid + 1), pz = __ldg(p.xyz + 3 * pid + 2);
+    const int64_t depth_elems = (int64_t)p.Hd * p.Wd;
+    const float wd_f = (float)p.Wd, hd_f = (float)p.Hd;
+    for (int c = 0; c < nchunks; ++c) {
+        const int v = p.v_begin + c * 32 + lane;
+        bool visible = false;
+        if (v < p.v_end) {
+            const float4 k4 = ldg_f4(p.K4 + 4 * (int64_t)v);
+            const float4 r0 = ldg_f4(p.w2c + 12 * (int64_t)v);
+            const float4 r1 = ldg_f4(p.w2c + 12 * (int64_t)v + 4);
+            const float4 r2 = ldg_f4(p.w2c + 12 * (int64_t)v + 8);
+            float uu, ww;
+            const float zc = project_point(k4, r0, r1, r2, px, py, pz, p.z_near, uu, ww);
+            int pix = -1;
+            if (zc > p.z_near) {
+                const float uif = floorf(__fadd_rn(uu, 0.5f));
+                const float wif = floorf(__fadd_rn(ww, 0.5f));
+                if (uif >= 0.f && uif < wd_f && wif >= 0.f && wif < hd_f) {
+                    const int cand = (int)wif * p.Wd + (int)uif;
+                    float d;
+                    if (p.depth_u16)
+                        d = __fmul_rn((float)__ldg(reinterpret_cast<const uint16_t*>(p.depth) + (int64_t)v * depth_elems + cand),
+                                      0.001f);
+                    else
+                        d = __ldg(reinterpret_cast<const float*>(p.depth) + (int64_t)v * depth_elems + cand);
+                    if (d > 0.f && fabsf(__fsub_rn(d, zc)) <= p.tau) {
+                        visible = true;
+                        pix = cand;
+                    }
+                }
+            }
+            if (p.pix_idx) p.pix_idx[(int64_t)v * p.N + pid] = pix;
+            if (p.vis) p.vis[(int64_t)v * p.N + pid] = visible ? 1 : 0;
+        }
+        const unsigned m = __ballot_sync(kFull, visible);
+        if (lane == 0) masks[pid * nchunks + c] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: bilinear gather + view sum + mean (+ run partial for the fused superpoint pooling), steps a-2/a-3.
+// CTA = 4 warps = one run of <= `run` consecutive points of the processing order; warp w takes points
+// w, w+4, ... of the run (neighbouring points at the same time -> shared L1 lines). Per point, lane r
+// re-projects the r-th visible view (cheap ALU, no depth read), then the warp walks the samples in
+// ascending view order with LANE = CHANNEL VECTOR and a two-deep register prefetch (sample i+1's tap
+// rows are in flight while sample i is blended).
+// ---------------------------------------------------------------------------------------------------
+template <int NV, typename FT, bool FAST, bool PREFETCH>
+__global__ void __launch_bounds__(kLiftThreads) gather_kernel(const LiftParams p, const uint32_t* __restrict__ masks,
+                                                              int nchunks) {
+    __shared__ float4 s_red[kLiftWarps][NV * 32];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int64_t task = blockIdx.x;
     int64_t start, end;
     int seg = -1;
     if (p.pool) {
@@ -135,136 +228,115 @@ __global__ void __launch_bounds__(kLiftThreads) lift_kernel(const LiftParams p) 
     }
     const FT* __restrict__ fmap = reinterpret_cast<const FT*>(p.fmap);
     const int64_t view_elems = (int64_t)p.Hf * p.Wf * p.C;
-    const int64_t depth_elems = (int64_t)p.Hd * p.Wd;
-    const float wd_f = (float)p.Wd, hd_f = (float)p.Hd;
 
     float4 sp_acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) sp_acc[k] = f4_zero();
 
-    for (int64_t g0 = start; g0 < end; g0 += G) {
-        int32_t pid[G];
-        float px[G], py[G], pz[G];
-        float4 acc[G][NV];
-        int cnt[G];
+    for (int64_t i = start + warp; i < end; i += kLiftWarps) {
+        const int32_t pid = p.order ? p.order[i] : (int32_t)i;
+        const float px = __ldg(p.xyz + 3 * (int64_t)pid), py = __ldg(p.xyz + 3 * (int64_t)pid + 1),
+                    pz = __ldg(p.xyz + 3 * (int64_t)pid + 2);
+        const uint32_t* __restrict__ mw = masks + (int64_t)pid * nchunks;
+        int n_total = 0;
+        for (int c = 0; c < nchunks; ++c) n_total += __popc(__ldg(mw + c));
+        float4 acc[NV];
 #pragma unroll
-        for (int j = 0; j < G; ++j) {
-            pid[j] = -1;
-            px[j] = py[j] = pz[j] = 0.f;
-            cnt[j] = 0;
-            if (g0 + j < end) {
-                pid[j] = p.order ? p.order[g0 + j] : (int32_t)(g0 + j);
-                px[j] = __ldg(p.xyz + 3 * (int64_t)pid[j]);
-                py[j] = __ldg(p.xyz + 3 * (int64_t)pid[j] + 1);
-                pz[j] = __ldg(p.xyz + 3 * (int64_t)pid[j] + 2);
-            }
+        for (int k = 0; k < NV; ++k) acc[k] = f4_zero();
+        int cnt = n_total;
+        if (p.accumulate) {
+            cnt += p.count[pid];
 #pragma unroll
-            for (int k = 0; k < NV; ++k) acc[j][k] = f4_zero();
-            if (p.accumulate && pid[j] >= 0) {
-                cnt[j] = p.count[pid[j]];
-#pragma unroll
-                for (int k = 0; k < NV; ++k) {
-                    const int c = (k * 32 + lane) * 4;
-                    if (c < p.C) acc[j][k] = *reinterpret_cast<const float4*>(p.out + (int64_t)pid[j] * p.C + c);
-                }
+            for (int k = 0; k < NV; ++k) {
+                const int c = (k * 32 + lane) * 4;
+                if (c < p.C) acc[k] = *reinterpret_cast<const float4*>(p.out + (int64_t)pid * p.C + c);
             }
         }
-
-        for (int v0 = p.v_begin; v0 < p.v_end; v0 += 32) {
-            const int v = v0 + lane;
-            const bool vok = v < p.v_end;
-            float4 k4 = f4_zero(), r0 = f4_zero(), r1 = f4_zero(), r2 = f4_zero();
-            if (vok) {
-                k4 = ldg_f4(p.K4 + 4 * (int64_t)v);
-                r0 = ldg_f4(p.w2c + 12 * (int64_t)v);
-                r1 = ldg_f4(p.w2c + 12 * (int64_t)v + 4);
-                r2 = ldg_f4(p.w2c + 12 * (int64_t)v + 8);
-            }
-            float us[G], ws[G];
-            unsigned mask[G];
-            unsigned any = 0u;
-#pragma unroll
-            for (int j = 0; j < G; ++j) {
-                bool visible = false;
-                float uu = 0.f, ww = 0.f;
-                int pix = -1;
-                if (vok && pid[j] >= 0) {
-                    const float xc = __fadd_rn(
-                        __fadd_rn(__fadd_rn(__fmul_rn(r0.x, px[j]), __fmul_rn(r0.y, py[j])), __fmul_rn(r0.z, pz[j])),
-                        r0.w);
-                    const float yc = __fadd_rn(
-                        __fadd_rn(__fadd_rn(__fmul_rn(r1.x, px[j]), __fmul_rn(r1.y, py[j])), __fmul_rn(r1.z, pz[j])),
-                        r1.w);
-                    const float zc = __fadd_rn(
-                        __fadd_rn(__fadd_rn(__fmul_rn(r2.x, px[j]), __fmul_rn(r2.y, py[j])), __fmul_rn(r2.z, pz[j])),
-                        r2.w);
-                    if (zc > p.z_near) {
-                        uu = __fadd_rn(__fdiv_rn(__fmul_rn(k4.x, xc), zc), k4.z);
-                        ww = __fadd_rn(__fdiv_rn(__fmul_rn(k4.y, yc), zc), k4.w);
-                        const float uif = floorf(__fadd_rn(uu, 0.5f));
-                        const float wif = floorf(__fadd_rn(ww, 0.5f));
-                        if (uif >= 0.f && uif < wd_f && wif >= 0.f && wif < hd_f) {
-                            const int cand = (int)wif * p.Wd + (int)uif;
-                            float d;
-                            if (p.depth_u16)
-                                d = __fmul_rn((float)__ldg(reinterpret_cast<const uint16_t*>(p.depth) +
-                                                           (int64_t)v * depth_elems + cand),
-                                              0.001f);
-                            else
-                                d = __ldg(reinterpret_cast<const float*>(p.depth) + (int64_t)v * depth_elems + cand);
-                            if (d > 0.f && fabsf(__fsub_rn(d, zc)) <= p.tau) {
-                                visible = true;
-                                pix = cand;
-                            }
+        for (int r0 = 0; r0 < n_total; r0 += 32) {
+            // lane r owns the (r0+r)-th visible view of this point (ascending view order)
+            int my_view = -1;
+            float my_u = 0.f, my_w = 0.f;
+            {
+                int rem = r0 + lane;
+                if (rem < n_total) {
+                    for (int c = 0; c < nchunks; ++c) {
+                        const uint32_t m = __ldg(mw + c);
+                        const int pc = __popc(m);
+                        if (rem < pc) {
+                            my_view = p.v_begin + c * 32 + (int)__fns(m, 0, rem + 1);
+                            break;
                         }
-                    }
-                    if (p.pix_idx) p.pix_idx[(int64_t)v * p.N + pid[j]] = pix;
-                    if (p.vis) p.vis[(int64_t)v * p.N + pid[j]] = visible ? 1 : 0;
-                }
-                us[j] = uu;
-                ws[j] = ww;
-                mask[j] = __ballot_sync(kFull, visible);
-                any |= mask[j];
-            }
-            while (any) {
-                const int b = __ffs(any) - 1;
-                any &= any - 1u;
-                const FT* __restrict__ fmap_v = fmap + (int64_t)(v0 + b) * view_elems;
-#pragma unroll
-                for (int j = 0; j < G; ++j) {
-                    if ((mask[j] >> b) & 1u) {
-                        const float uu = __shfl_sync(kFull, us[j], b);
-                        const float ww = __shfl_sync(kFull, ws[j], b);
-                        gather_sample<NV, FT>(acc[j], fmap_v, uu, ww, p.stride, p.Hf, p.Wf, p.C, lane);
+                        rem -= pc;
                     }
                 }
+                if (my_view >= 0) {
+                    const float4 k4 = ldg_f4(p.K4 + 4 * (int64_t)my_view);
+                    const float4 q0 = ldg_f4(p.w2c + 12 * (int64_t)my_view);
+                    const float4 q1 = ldg_f4(p.w2c + 12 * (int64_t)my_view + 4);
+                    const float4 q2 = ldg_f4(p.w2c + 12 * (int64_t)my_view + 8);
+                    project_point(k4, q0, q1, q2, px, py, pz, p.z_near, my_u, my_w);
+                }
             }
-#pragma unroll
-            for (int j = 0; j < G; ++j) cnt[j] += __popc(mask[j]);
+            const int n_round = min(32, n_total - r0);
+            if (PREFETCH) {
+                Sample<NV> sa, sb;
+                {
+                    const int v = __shfl_sync(kFull, my_view, 0);
+                    sample_issue<NV, FT>(sa, fmap + (int64_t)v * view_elems, __shfl_sync(kFull, my_u, 0),
+                                         __shfl_sync(kFull, my_w, 0), p.stride, p.Hf, p.Wf, p.C, lane);
+                }
+                int sidx = 0;
+                while (true) {
+                    if (sidx + 1 < n_round) {
+                        const int v = __shfl_sync(kFull, my_view, sidx + 1);
+                        sample_issue<NV, FT>(sb, fmap + (int64_t)v * view_elems, __shfl_sync(kFull, my_u, sidx + 1),
+                                             __shfl_sync(kFull, my_w, sidx + 1), p.stride, p.Hf, p.Wf, p.C, lane);
+                    }
+                    sample_accum<NV, FAST>(acc, sa);
+                    if (++sidx >= n_round) break;
+                    if (sidx + 1 < n_round) {
+                        const int v = __shfl_sync(kFull, my_view, sidx + 1);
+                        sample_issue<NV, FT>(sa, fmap + (int64_t)v * view_elems, __shfl_sync(kFull, my_u, sidx + 1),
+                                             __shfl_sync(kFull, my_w, sidx + 1), p.stride, p.Hf, p.Wf, p.C, lane);
+                    }
+                    sample_accum<NV, FAST>(acc, sb);
+                    if (++sidx >= n_round) break;
+                }
+            } else {  // wide rows (C > 512): one sample in flight, the tap rows alone fill the register file
+                Sample<NV> sa;
+                for (int sidx = 0; sidx < n_round; ++sidx) {
+                    const int v = __shfl_sync(kFull, my_view, sidx);
+                    sample_issue<NV, FT>(sa, fmap + (int64_t)v * view_elems, __shfl_sync(kFull, my_u, sidx),
+                                         __shfl_sync(kFull, my_w, sidx), p.stride, p.Hf, p.Wf, p.C, lane);
+                    sample_accum<NV, FAST>(acc, sa);
+                }
+            }
         }
-
-#pragma unroll
-        for (int j = 0; j < G; ++j) {
-            if (pid[j] >= 0) {
-                const float denom = (float)max(cnt[j], 1);
-#pragma unroll
-                for (int k = 0; k < NV; ++k) {
-                    const int c = (k * 32 + lane) * 4;
-                    if (c < p.C) {
-                        const float4 o = p.finalize ? f4_div(acc[j][k], denom) : acc[j][k];
-                        st_cs_f4(p.out + (int64_t)pid[j] * p.C + c, o);
-                        sp_acc[k] = f4_add(sp_acc[k], o);
-                    }
-                }
-                if (lane == 0) p.count[pid[j]] = cnt[j];
-            }
-        }
-    }
-    if (p.pool && seg < p.S) {
+        const float denom = (float)max(cnt, 1);
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const int c = (k * 32 + lane) * 4;
-            if (c < p.C) *reinterpret_cast<float4*>(p.partials + task * (int64_t)p.C + c) = sp_acc[k];
+            if (c < p.C) {
+                const float4 o = p.finalize ? f4_div(acc[k], denom) : acc[k];
+                st_cs_f4(p.out + (int64_t)pid * p.C + c, o);
+                sp_acc[k] = f4_add(sp_acc[k], o);
+            }
+        }
+        if (lane == 0) p.count[pid] = cnt;
+    }
+    if (p.pool && seg < p.S) {  // uniform per CTA
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s_red[warp][k * 32 + lane] = sp_acc[k];
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                float4 t = s_red[0][k * 32 + lane];
+#pragma unroll
+                for (int w = 1; w < kLiftWarps; ++w) t = f4_add(t, s_red[w][k * 32 + lane]);
+                const int c = (k * 32 + lane) * 4;
+                if (c < p.C) *reinterpret_cast<float4*>(p.partials + task * (int64_t)p.C + c) = t;
+            }
         }
     }
 }
@@ -318,42 +390,44 @@ __global__ void scale_mean_kernel(ScalePtrs ptrs, int L, int64_t numel, float* _
     }
 }
 
-template <int NV, typename FT, int G>
-static void launch_lift(const LiftParams& p, int64_t n_tasks, cudaStream_t stream) {
-    const unsigned grid = (unsigned)ceil_div64(n_tasks, kLiftWarps);
-    lift_kernel<NV, FT, G><<<grid, kLiftThreads, 0, stream>>>(p);
+template <int NV, typename FT>
+static void launch_gather(const LiftParams& p, const uint32_t* masks, int nchunks, int64_t n_tasks, bool fast,
+                          cudaStream_t stream) {
+    const unsigned grid = (unsigned)n_tasks;
+    constexpr bool kPrefetch = NV <= 4;
+    if (fast)
+        gather_kernel<NV, FT, true, kPrefetch><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
+    else
+        gather_kernel<NV, FT, false, kPrefetch><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
 }
 
 template <typename FT>
-static int dispatch_lift(const LiftParams& p, int64_t n_tasks, int variant, cudaStream_t stream) {
+static int dispatch_gather(const LiftParams& p, const uint32_t* masks, int nchunks, int64_t n_tasks, int variant,
+                           cudaStream_t stream) {
     const int nv = (p.C + 127) / 128;
-    if (nv == 1) {
-        launch_lift<1, FT, 8>(p, n_tasks, stream);
-    } else if (nv == 2) {
-        if constexpr (sizeof(FT) == 4) {
-            switch (variant) {
-                case 1: launch_lift<2, FT, 1>(p, n_tasks, stream); break;
-                case 2: launch_lift<2, FT, 2>(p, n_tasks, stream); break;
-                case 8: launch_lift<2, FT, 8>(p, n_tasks, stream); break;
-                default: launch_lift<2, FT, 4>(p, n_tasks, stream); break;
-            }
-        } else {
-            launch_lift<2, FT, 4>(p, n_tasks, stream);
-        }
-    } else if (nv <= 4) {
-        launch_lift<4, FT, 2>(p, n_tasks, stream);
-    } else if (nv <= 8) {
-        launch_lift<8, FT, 1>(p, n_tasks, stream);
-    } else {
+    const bool fast = (variant & 1) != 0;
+    if (nv == 1) launch_gather<1, FT>(p, masks, nchunks, n_tasks, fast, stream);
+    else if (nv == 2) launch_gather<2, FT>(p, masks, nchunks, n_tasks, fast, stream);
+    else if (nv <= 4) launch_gather<4, FT>(p, masks, nchunks, n_tasks, fast, stream);
+    else if (nv <= 8) launch_gather<8, FT>(p, masks, nchunks, n_tasks, fast, stream);
+    else {
         set_error("sd3d_lift: C=%d > 1024 unsupported", p.C);
         return SD3D_ERR_UNSUPPORTED;
     }
     return SD3D_OK;
 }
 
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
 }  // namespace sd3d
 
 using namespace sd3d;
+
+extern "C" size_t sd3d_lift_workspace_bytes(int64_t N, int n_views, int C, int64_t max_tasks) {
+    if (N < 0 || n_views < 0 || C < 0 || max_tasks < 0) return 0;
+    const size_t nchunks = (size_t)(n_views + 31) / 32;
+    return align_up((size_t)max_tasks * C * sizeof(float), 256) + align_up((size_t)N * nchunks * sizeof(uint32_t), 256) + 256;
+}
 
 extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin,
                          int view_end, const void* depth, int depth_dtype, int Hd, int Wd, const void* fmap,
@@ -393,13 +467,23 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
     if (run <= 0) run = 32;
     if (pool) {
         if (!finalize || order == nullptr || seg_offsets == nullptr || task_offsets == nullptr ||
-            task_seg == nullptr || ws == nullptr || S < 0 || max_tasks < sd3d_sp_max_tasks(N, S, run) ||
-            ws_bytes < (size_t)max_tasks * C * sizeof(float) || !aligned16(ws)) {
-            set_error("sd3d_lift: fused pooling needs finalize=1, order, seg_offsets, task tables and ws >= max_tasks*C*4");
+            task_seg == nullptr || S < 0 || max_tasks < sd3d_sp_max_tasks(N, S, run)) {
+            set_error("sd3d_lift: fused pooling needs finalize=1, order, seg_offsets and the task tables");
             return SD3D_ERR_ARG;
         }
+    } else {
+        max_tasks = 0;
     }
     if (N == 0) return SD3D_OK;  // task_offsets are all zero -> sd3d_sp_combine writes zero rows
+    const int n_views = view_end - view_begin;
+    const int nchunks = (n_views + 31) / 32;
+    if (ws == nullptr || !aligned16(ws) || ws_bytes < sd3d_lift_workspace_bytes(N, n_views, C, max_tasks)) {
+        set_error("sd3d_lift: workspace missing/misaligned/too small (%zu < %zu bytes)", ws_bytes,
+                  sd3d_lift_workspace_bytes(N, n_views, C, max_tasks));
+        return SD3D_ERR_ARG;
+    }
+    uint32_t* masks = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ws) +
+                                                  align_up((size_t)max_tasks * C * sizeof(float), 256));
     LiftParams p;
     p.xyz = xyz; p.N = N; p.K4 = K4; p.w2c = w2c; p.v_begin = view_begin; p.v_end = view_end;
     p.depth = depth; p.depth_u16 = depth_dtype == SD3D_U16; p.Hd = Hd; p.Wd = Wd;
@@ -409,11 +493,13 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
     p.task_offsets = task_offsets; p.task_seg = task_seg; p.S = (int32_t)S; p.run = run;
     p.partials = reinterpret_cast<float*>(ws);
     const int64_t n_tasks = pool ? max_tasks : ceil_div64(N, run);
+    if (nchunks > 0)
+        project_kernel<<<(unsigned)ceil_div64(N, kProjWarps), kProjThreads, 0, stream>>>(p, masks, nchunks);
     int rc;
     switch (fmap_dtype) {
-        case SD3D_F32: rc = dispatch_lift<float>(p, n_tasks, variant, stream); break;
-        case SD3D_F16: rc = dispatch_lift<__half>(p, n_tasks, variant, stream); break;
-        case SD3D_BF16: rc = dispatch_lift<__nv_bfloat16>(p, n_tasks, variant, stream); break;
+        case SD3D_F32: rc = dispatch_gather<float>(p, masks, nchunks, n_tasks, variant, stream); break;
+        case SD3D_F16: rc = dispatch_gather<__half>(p, masks, nchunks, n_tasks, variant, stream); break;
+        case SD3D_BF16: rc = dispatch_gather<__nv_bfloat16>(p, masks, nchunks, n_tasks, variant, stream); break;
         default:
             set_error("sd3d_lift: fmap dtype code %d unsupported", fmap_dtype);
             return SD3D_ERR_UNSUPPORTED;

@@ -159,7 +159,7 @@ def scatter_mean(src: torch.Tensor, index: torch.Tensor, dim: int = -1, out: Opt
     if not src.is_floating_point():
         raise Sd3dError("scatter_mean drop-in covers floating-point src only")
     squeeze = src.dim() == 1
-    src2 = src.reshape(src.shape[0], -1)
+    src2 = src.reshape(src.shape[0], 1 if src.dim() == 1 else src.shape[1])
     orig_dtype = src2.dtype
     if orig_dtype != torch.float32:
         src2 = src2.float()
@@ -244,15 +244,14 @@ def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Ten
         if want_maps:
             pix = torch.full((v, n), -1, dtype=torch.int32, device=dev)
             vis = torch.zeros((v, n), dtype=torch.uint8, device=dev)
-        sp_out = ws = None
-        ws_bytes = 0
+        sp_out = None
         s = 0
         if plan is not None:
             s = plan.n_segments
         if pool:
             sp_out = torch.empty(s, c, dtype=torch.float32, device=dev)
-            ws_bytes = plan.max_tasks * c * 4
-            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        ws_bytes = int(lib.sd3d_lift_workspace_bytes(n, ve - vb, c, plan.max_tasks if pool else 0))
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
         if events is not None:
             events[0].record()
         check(lib.sd3d_lift(_ptr(xyz), n, _ptr(K), _ptr(w2c), v, vb, ve, _ptr(depth), _DEPTH_CODE[depth.dtype], hd, wd,
