@@ -234,7 +234,7 @@ def run_ours(args):
     b_lift, b_path = algorithmic_bytes(n, v, wl["hd"], wl["wd"], hf, wf, c, scenes[0].n_superpoints)
 
     def step(sc, events=None):
-        plan = sd.sp_sort(sc.sp_ids, sc.n_superpoints, run=args.run)
+        plan = sd.sp_sort(sc.sp_ids, sc.n_superpoints, run=args.run, xyz=None if args.no_refine else sc.xyz)
         r = sd.lift(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride, plan=plan, pool=True, variant=args.variant,
                     events=events)
         return r
@@ -282,7 +282,7 @@ def run_ours(args):
 
         def e2e_step(h, sc_meta):
             dv = {k: t.to(dev, non_blocking=True) for k, t in h.items()}
-            plan = sd.sp_sort(dv["sp_ids"], sc_meta.n_superpoints, run=args.run)
+            plan = sd.sp_sort(dv["sp_ids"], sc_meta.n_superpoints, run=args.run, xyz=None if args.no_refine else dv["xyz"])
             r = sd.lift(dv["xyz"], dv["K"], dv["w2c"], dv["depth"], dv["fmap"], sc_meta.stride, plan=plan, pool=True,
                         variant=args.variant)
             out_feat.copy_(r["feat"], non_blocking=True)
@@ -327,7 +327,7 @@ def run_ours(args):
                          "path_algorithmic_bytes": b_path,
                          "path_frac": b_path / (ms_per_step * 1e-3) / 1e9 / peak},
             "clocks": clocks,
-            "gpu_launches": 6 * args.steps,
+            "gpu_launches": (7 if args.no_refine else 8) * args.steps,
         }
         if e2e is not None:
             line["e2e"] = e2e
@@ -350,6 +350,7 @@ def main():
     ap.add_argument("--rotate", type=int, default=4, help="distinct scenes cycled through (defeats L2 residency)")
     ap.add_argument("--run", type=int, default=32, help="points per warp run")
     ap.add_argument("--variant", type=int, default=0, help="points-per-warp group (0=default, 1/2/4/8)")
+    ap.add_argument("--no-refine", action="store_true", help="skip the Morton refinement of the processing order")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -57,12 +57,19 @@ int sd3d_sp_sort(const int64_t* idx, int64_t N, int64_t S, int32_t* perm, int32_
                  size_t ws_bytes, void* stream);
 
 /* Splits every superpoint into runs of <= `run` consecutive sorted points (the unit one warp reduces).
- * task_offsets[S+2]: superpoint s owns tasks [task_offsets[s], task_offsets[s+1]); task_seg[t] = s
- * (segment S = the invalid-id points, which are lifted but never pooled).
+ * task_offsets[S+2]: superpoint s owns the ceil(n_s/run) tasks starting at task_offsets[s]; task_seg[t] = s
+ * (segment S = the invalid-id points, which are lifted but never pooled); task_offsets[S+1] = task count.
  * max_tasks = sd3d_sp_max_tasks(N,S,run) is the size the caller must give task_seg. */
 int64_t sd3d_sp_max_tasks(int64_t N, int64_t S, int run);
-int sd3d_sp_tasks(const int32_t* seg_offsets, int64_t S, int run, int32_t* task_offsets, int32_t* task_seg,
-                  int64_t max_tasks, void* stream);
+int sd3d_sp_tasks(const int32_t* seg_offsets, const uint32_t* anchor /*nullable*/, int64_t S, int run,
+                  int32_t* task_offsets, int32_t* task_seg, int64_t max_tasks, void* stream);
+
+/* Spatial refinement of the processing order (cache locality only -- results never depend on it):
+ * order[N] = perm with the points of every superpoint re-ordered along a Morton curve; anchor[S+1] = one
+ * world-grid Morton key per superpoint, which sd3d_sp_tasks uses to lay the runs out along the same curve.
+ * xyz[N,3] f32 as given to sd3d_lift. No reference counterpart (the reference gathers nothing). */
+int sd3d_sp_refine(const float* xyz, const int32_t* perm, const int32_t* seg_offsets, int64_t N, int64_t S,
+                   int32_t* order, uint32_t* anchor, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a-4: out[s,:] = sum_{p in s} src[p,:] / max(|s|,1)    == scatter_mean(src, idx, dim=0)
@@ -109,7 +116,7 @@ int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, in
 
 /* second half of the fused pooling: sp_out[s,:] = (sum of the run partials of s, in run order) / max(|s|,1) */
 int sd3d_sp_combine(const void* partials, const int32_t* task_offsets, const int32_t* seg_offsets, int64_t S, int C,
-                    float* sp_out, void* stream);
+                    int run, float* sp_out, void* stream);
 
 /* feat = sum / (float)max(count,1) in place (Appendix A `feat_l`); used after the multi-GPU all-reduce */
 int sd3d_lift_finalize(float* sum_inout, const int32_t* count, int64_t N, int C, void* stream);

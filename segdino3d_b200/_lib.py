@@ -23,7 +23,8 @@ SYMBOLS = {
     "sd3d_sp_sort_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "sd3d_sp_sort": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sd3d_sp_max_tasks": (c_int64, [c_int64, c_int64, c_int]),
-    "sd3d_sp_tasks": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "sd3d_sp_tasks": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "sd3d_sp_refine": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
     "sd3d_sp_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p,
                              c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "sd3d_lift_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int64]),
@@ -34,7 +35,7 @@ SYMBOLS = {
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,                # order out count pix vis
                           c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,           # seg_off S task_off task_seg max_tasks run
                           c_void_p, c_size_t, c_int, c_int, c_void_p]),                    # ws ws_bytes pool variant stream
-    "sd3d_sp_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "sd3d_sp_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "sd3d_lift_finalize": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "sd3d_scale_mean": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "sd3d_mask_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p,

@@ -92,34 +92,77 @@ struct Sample {
     float4 t00[NV], t01[NV], t10[NV], t11[NV];
 };
 
-// issue the 4*NV 128-bit loads of one sample (no use of the data here -> they stay in flight)
-template <int NV, typename FT>
-__device__ __forceinline__ void sample_issue(Sample<NV>& s, const FT* __restrict__ fmap_v, float u, float w,
-                                             float stride, int Hf, int Wf, int C, int lane) {
+// Per-sample scalars, computed ONCE by the lane that owns the sample (Appendix A lines `uf = ...` ..
+// `w11 = ...`) and broadcast with shuffles: in-view element offset of tap (y0,x0), the four weights, and
+// which taps fall inside the map (bits 0..3 = t00,t01,t10,t11).
+struct SampleScalars {
+    int view_flags;  // view index | tap-valid bits << 24
+    int o00;         // ((y0*Wf)+x0)*C, may be negative when the tap is outside (then its bit is clear)
+    float w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ SampleScalars make_scalars(int view, float u, float w, float stride, int Hf, int Wf,
+                                                      int C) {
+    SampleScalars r;
     const float uf = __fsub_rn(__fdiv_rn(__fadd_rn(u, 0.5f), stride), 0.5f);
     const float wf = __fsub_rn(__fdiv_rn(__fadd_rn(w, 0.5f), stride), 0.5f);
     const float x0f = floorf(uf), y0f = floorf(wf);
     const float ax = __fsub_rn(uf, x0f), ay = __fsub_rn(wf, y0f);
     const int x0 = (int)x0f, y0 = (int)y0f;
     const float omx = __fsub_rn(1.0f, ax), omy = __fsub_rn(1.0f, ay);
-    s.w00 = __fmul_rn(omx, omy);
-    s.w01 = __fmul_rn(ax, omy);
-    s.w10 = __fmul_rn(omx, ay);
-    s.w11 = __fmul_rn(ax, ay);
+    r.w00 = __fmul_rn(omx, omy);
+    r.w01 = __fmul_rn(ax, omy);
+    r.w10 = __fmul_rn(omx, ay);
+    r.w11 = __fmul_rn(ax, ay);
     const bool okx0 = (x0 >= 0) && (x0 < Wf), okx1 = (x0 + 1 >= 0) && (x0 + 1 < Wf);
     const bool oky0 = (y0 >= 0) && (y0 < Hf), oky1 = (y0 + 1 >= 0) && (y0 + 1 < Hf);
-    const bool ok00 = oky0 && okx0, ok01 = oky0 && okx1, ok10 = oky1 && okx0, ok11 = oky1 && okx1;
-    const int64_t o00 = ((int64_t)y0 * Wf + x0) * C;
-    const int64_t o01 = o00 + C, o10 = o00 + (int64_t)Wf * C, o11 = o10 + C;
+    const int flags = (int)(oky0 && okx0) | ((int)(oky0 && okx1) << 1) | ((int)(oky1 && okx0) << 2) |
+                      ((int)(oky1 && okx1) << 3);
+    r.view_flags = view | (flags << 24);
+    r.o00 = (y0 * Wf + x0) * C;
+    return r;
+}
+
+// issue the 4*NV 128-bit loads of sample `src_lane` (no use of the data here -> they stay in flight)
+template <int NV, typename FT>
+__device__ __forceinline__ void sample_issue(Sample<NV>& s, const SampleScalars& mine, int src_lane,
+                                             const FT* __restrict__ fmap, int64_t view_elems, int C, int row_elems,
+                                             int lane) {
+    const int vf = __shfl_sync(kFull, mine.view_flags, src_lane);
+    const int o00 = __shfl_sync(kFull, mine.o00, src_lane);
+    s.w00 = __shfl_sync(kFull, mine.w00, src_lane);
+    s.w01 = __shfl_sync(kFull, mine.w01, src_lane);
+    s.w10 = __shfl_sync(kFull, mine.w10, src_lane);
+    s.w11 = __shfl_sync(kFull, mine.w11, src_lane);
+    const int flags = (vf >> 24) & 0xF;
+    const FT* __restrict__ p00 = fmap + (int64_t)(vf & 0xFFFFFF) * view_elems + o00 + lane * 4;
+    const FT* __restrict__ p10 = p00 + row_elems;
+    if (flags == 0xF) {  // interior sample (the common case): unpredicated-on-validity loads
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const int c = (k * 32 + lane) * 4;
-        const bool cok = c < C;
-        s.t00[k] = (cok && ok00) ? load_tap<FT>(fmap_v + o00 + c) : f4_zero();
-        s.t01[k] = (cok && ok01) ? load_tap<FT>(fmap_v + o01 + c) : f4_zero();
-        s.t10[k] = (cok && ok10) ? load_tap<FT>(fmap_v + o10 + c) : f4_zero();
-        s.t11[k] = (cok && ok11) ? load_tap<FT>(fmap_v + o11 + c) : f4_zero();
+        for (int k = 0; k < NV; ++k) {
+            if ((k * 32 + lane) * 4 < C) {
+                s.t00[k] = load_tap<FT>(p00 + k * 128);
+                s.t01[k] = load_tap<FT>(p00 + C + k * 128);
+                s.t10[k] = load_tap<FT>(p10 + k * 128);
+                s.t11[k] = load_tap<FT>(p10 + C + k * 128);
+            }
+        }
+    } else {  // border sample: taps outside the map read as zero (Appendix A `tap(y,x)`)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const bool cok = (k * 32 + lane) * 4 < C;
+            s.t00[k] = (cok && (flags & 1)) ? load_tap<FT>(p00 + k * 128) : f4_zero();
+            s.t01[k] = (cok && (flags & 2)) ? load_tap<FT>(p00 + C + k * 128) : f4_zero();
+            s.t10[k] = (cok && (flags & 4)) ? load_tap<FT>(p10 + k * 128) : f4_zero();
+            s.t11[k] = (cok && (flags & 8)) ? load_tap<FT>(p10 + C + k * 128) : f4_zero();
+        }
     }
+}
+
+template <int NV>
+__device__ __forceinline__ void sample_clear(Sample<NV>& s) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s.t00[k] = s.t01[k] = s.t10[k] = s.t11[k] = f4_zero();
 }
 
 template <int NV, bool FAST>
@@ -154,48 +197,68 @@ __device__ __forceinline__ float project_point(const float4 k4, const float4 r0,
 // ---------------------------------------------------------------------------------------------------
 constexpr int kProjThreads = 256;
 constexpr int kProjWarps = kProjThreads / 32;
+constexpr int kProjPts = 4;  // points per warp: 4 independent depth reads in flight per lane
 
 __global__ void __launch_bounds__(kProjThreads) project_kernel(const LiftParams p, uint32_t* __restrict__ masks,
                                                                int nchunks) {
     const int lane = lane_id();
-    const int64_t pid = (int64_t)blockIdx.x * kProjWarps + (threadIdx.x >> 5);
-    if (pid >= p.N) return;
-    const float px = __ldg(p.xyz + 3 * pid), py = __ldg(p.xyz + 3 * pid + 1), pz = __ldg(p.xyz + 3 * pid + 2);
+    const int64_t p0 = ((int64_t)blockIdx.x * kProjWarps + (threadIdx.x >> 5)) * kProjPts;
+    if (p0 >= p.N) return;
+    float px[kProjPts], py[kProjPts], pz[kProjPts];
+#pragma unroll
+    for (int j = 0; j < kProjPts; ++j) {
+        const int64_t pid = min(p0 + j, p.N - 1);
+        px[j] = __ldg(p.xyz + 3 * pid);
+        py[j] = __ldg(p.xyz + 3 * pid + 1);
+        pz[j] = __ldg(p.xyz + 3 * pid + 2);
+    }
     const int64_t depth_elems = (int64_t)p.Hd * p.Wd;
     const float wd_f = (float)p.Wd, hd_f = (float)p.Hd;
     for (int c = 0; c < nchunks; ++c) {
         const int v = p.v_begin + c * 32 + lane;
-        bool visible = false;
-        if (v < p.v_end) {
-            const float4 k4 = ldg_f4(p.K4 + 4 * (int64_t)v);
-            const float4 r0 = ldg_f4(p.w2c + 12 * (int64_t)v);
-            const float4 r1 = ldg_f4(p.w2c + 12 * (int64_t)v + 4);
-            const float4 r2 = ldg_f4(p.w2c + 12 * (int64_t)v + 8);
-            float uu, ww;
-            const float zc = project_point(k4, r0, r1, r2, px, py, pz, p.z_near, uu, ww);
-            int pix = -1;
-            if (zc > p.z_near) {
-                const float uif = floorf(__fadd_rn(uu, 0.5f));
-                const float wif = floorf(__fadd_rn(ww, 0.5f));
-                if (uif >= 0.f && uif < wd_f && wif >= 0.f && wif < hd_f) {
-                    const int cand = (int)wif * p.Wd + (int)uif;
-                    float d;
-                    if (p.depth_u16)
-                        d = __fmul_rn((float)__ldg(reinterpret_cast<const uint16_t*>(p.depth) + (int64_t)v * depth_elems + cand),
-                                      0.001f);
-                    else
-                        d = __ldg(reinterpret_cast<const float*>(p.depth) + (int64_t)v * depth_elems + cand);
-                    if (d > 0.f && fabsf(__fsub_rn(d, zc)) <= p.tau) {
-                        visible = true;
-                        pix = cand;
+        const bool vok = v < p.v_end;
+        float4 k4 = f4_zero(), r0 = f4_zero(), r1 = f4_zero(), r2 = f4_zero();
+        if (vok) {
+            k4 = ldg_f4(p.K4 + 4 * (int64_t)v);
+            r0 = ldg_f4(p.w2c + 12 * (int64_t)v);
+            r1 = ldg_f4(p.w2c + 12 * (int64_t)v + 4);
+            r2 = ldg_f4(p.w2c + 12 * (int64_t)v + 8);
+        }
+        float zc[kProjPts], d[kProjPts];
+        int cand[kProjPts];
+#pragma unroll
+        for (int j = 0; j < kProjPts; ++j) {  // phase 1: project, issue the depth reads
+            cand[j] = -1;
+            d[j] = 0.f;
+            zc[j] = 0.f;
+            if (vok && p0 + j < p.N) {
+                float uu, ww;
+                zc[j] = project_point(k4, r0, r1, r2, px[j], py[j], pz[j], p.z_near, uu, ww);
+                if (zc[j] > p.z_near) {
+                    const float uif = floorf(__fadd_rn(uu, 0.5f));
+                    const float wif = floorf(__fadd_rn(ww, 0.5f));
+                    if (uif >= 0.f && uif < wd_f && wif >= 0.f && wif < hd_f) {
+                        cand[j] = (int)wif * p.Wd + (int)uif;
+                        if (p.depth_u16)
+                            d[j] = __fmul_rn((float)__ldg(reinterpret_cast<const uint16_t*>(p.depth) +
+                                                          (int64_t)v * depth_elems + cand[j]),
+                                             0.001f);
+                        else
+                            d[j] = __ldg(reinterpret_cast<const float*>(p.depth) + (int64_t)v * depth_elems + cand[j]);
                     }
                 }
             }
-            if (p.pix_idx) p.pix_idx[(int64_t)v * p.N + pid] = pix;
-            if (p.vis) p.vis[(int64_t)v * p.N + pid] = visible ? 1 : 0;
         }
-        const unsigned m = __ballot_sync(kFull, visible);
-        if (lane == 0) masks[pid * nchunks + c] = m;
+#pragma unroll
+        for (int j = 0; j < kProjPts; ++j) {  // phase 2: depth test, pack the predicate
+            const bool visible = cand[j] >= 0 && d[j] > 0.f && fabsf(__fsub_rn(d[j], zc[j])) <= p.tau;
+            if (vok && p0 + j < p.N) {
+                if (p.pix_idx) p.pix_idx[(int64_t)v * p.N + p0 + j] = visible ? cand[j] : -1;
+                if (p.vis) p.vis[(int64_t)v * p.N + p0 + j] = visible ? 1 : 0;
+            }
+            const unsigned m = __ballot_sync(kFull, visible);
+            if (lane == 0 && p0 + j < p.N) masks[(p0 + j) * nchunks + c] = m;
+        }
     }
 }
 
@@ -228,10 +291,14 @@ __global__ void __launch_bounds__(kLiftThreads) gather_kernel(const LiftParams p
     }
     const FT* __restrict__ fmap = reinterpret_cast<const FT*>(p.fmap);
     const int64_t view_elems = (int64_t)p.Hf * p.Wf * p.C;
+    const int row_elems = p.Wf * p.C;
 
     float4 sp_acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) sp_acc[k] = f4_zero();
+    Sample<NV> sa, sb;  // lanes beyond C never load: give their registers a defined value once
+    sample_clear<NV>(sa);
+    sample_clear<NV>(sb);
 
     for (int64_t i = start + warp; i < end; i += kLiftWarps) {
         const int32_t pid = p.order ? p.order[i] : (int32_t)i;
@@ -253,10 +320,14 @@ __global__ void __launch_bounds__(kLiftThreads) gather_kernel(const LiftParams p
             }
         }
         for (int r0 = 0; r0 < n_total; r0 += 32) {
-            // lane r owns the (r0+r)-th visible view of this point (ascending view order)
-            int my_view = -1;
-            float my_u = 0.f, my_w = 0.f;
+            // lane r owns the (r0+r)-th visible view of this point (ascending view order) and computes that
+            // sample's scalars once (re-projection needs no depth read: visibility is already in the mask)
+            SampleScalars mine;
+            mine.view_flags = 0;
+            mine.o00 = 0;
+            mine.w00 = mine.w01 = mine.w10 = mine.w11 = 0.f;
             {
+                int my_view = -1;
                 int rem = r0 + lane;
                 if (rem < n_total) {
                     for (int c = 0; c < nchunks; ++c) {
@@ -274,40 +345,26 @@ __global__ void __launch_bounds__(kLiftThreads) gather_kernel(const LiftParams p
                     const float4 q0 = ldg_f4(p.w2c + 12 * (int64_t)my_view);
                     const float4 q1 = ldg_f4(p.w2c + 12 * (int64_t)my_view + 4);
                     const float4 q2 = ldg_f4(p.w2c + 12 * (int64_t)my_view + 8);
+                    float my_u, my_w;
                     project_point(k4, q0, q1, q2, px, py, pz, p.z_near, my_u, my_w);
+                    mine = make_scalars(my_view, my_u, my_w, p.stride, p.Hf, p.Wf, p.C);
                 }
             }
             const int n_round = min(32, n_total - r0);
             if (PREFETCH) {
-                Sample<NV> sa, sb;
-                {
-                    const int v = __shfl_sync(kFull, my_view, 0);
-                    sample_issue<NV, FT>(sa, fmap + (int64_t)v * view_elems, __shfl_sync(kFull, my_u, 0),
-                                         __shfl_sync(kFull, my_w, 0), p.stride, p.Hf, p.Wf, p.C, lane);
-                }
+                sample_issue<NV, FT>(sa, mine, 0, fmap, view_elems, p.C, row_elems, lane);
                 int sidx = 0;
                 while (true) {
-                    if (sidx + 1 < n_round) {
-                        const int v = __shfl_sync(kFull, my_view, sidx + 1);
-                        sample_issue<NV, FT>(sb, fmap + (int64_t)v * view_elems, __shfl_sync(kFull, my_u, sidx + 1),
-                                             __shfl_sync(kFull, my_w, sidx + 1), p.stride, p.Hf, p.Wf, p.C, lane);
-                    }
+                    if (sidx + 1 < n_round) sample_issue<NV, FT>(sb, mine, sidx + 1, fmap, view_elems, p.C, row_elems, lane);
                     sample_accum<NV, FAST>(acc, sa);
                     if (++sidx >= n_round) break;
-                    if (sidx + 1 < n_round) {
-                        const int v = __shfl_sync(kFull, my_view, sidx + 1);
-                        sample_issue<NV, FT>(sa, fmap + (int64_t)v * view_elems, __shfl_sync(kFull, my_u, sidx + 1),
-                                             __shfl_sync(kFull, my_w, sidx + 1), p.stride, p.Hf, p.Wf, p.C, lane);
-                    }
+                    if (sidx + 1 < n_round) sample_issue<NV, FT>(sa, mine, sidx + 1, fmap, view_elems, p.C, row_elems, lane);
                     sample_accum<NV, FAST>(acc, sb);
                     if (++sidx >= n_round) break;
                 }
             } else {  // wide rows (C > 512): one sample in flight, the tap rows alone fill the register file
-                Sample<NV> sa;
                 for (int sidx = 0; sidx < n_round; ++sidx) {
-                    const int v = __shfl_sync(kFull, my_view, sidx);
-                    sample_issue<NV, FT>(sa, fmap + (int64_t)v * view_elems, __shfl_sync(kFull, my_u, sidx),
-                                         __shfl_sync(kFull, my_w, sidx), p.stride, p.Hf, p.Wf, p.C, lane);
+                    sample_issue<NV, FT>(sa, mine, sidx, fmap, view_elems, p.C, row_elems, lane);
                     sample_accum<NV, FAST>(acc, sa);
                 }
             }
@@ -341,28 +398,39 @@ __global__ void __launch_bounds__(kLiftThreads) gather_kernel(const LiftParams p
     }
 }
 
-// out[s,:] = (P[t0] + P[t0+1] + ... in task order) / max(n_s,1)
-__global__ void sp_combine_kernel(const float* __restrict__ partials, const int32_t* __restrict__ task_offsets,
-                                  const int32_t* __restrict__ seg_offsets, int32_t S, int C,
-                                  float* __restrict__ out) {
+// out[s,:] = (sum of the run partials of s) / max(n_s,1). Eight lanes share one (superpoint, channel
+// vector): lane j adds partials t0+j, t0+j+8, ... in order, then the eight lane sums are added in lane
+// order -> a fixed summation tree (deterministic), 8x shorter dependent-load chains than a serial walk.
+__global__ void __launch_bounds__(256) sp_combine_kernel(const float* __restrict__ partials,
+                                                         const int32_t* __restrict__ task_offsets,
+                                                         const int32_t* __restrict__ seg_offsets, int32_t S, int C,
+                                                         int run, float* __restrict__ out) {
     const int vec_per_row = C >> 2;
-    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (int64_t)S * vec_per_row) return;
-    const int s = (int)(gid / vec_per_row);
-    const int c = (int)(gid % vec_per_row) * 4;
-    const int t0 = task_offsets[s], t1 = task_offsets[s + 1];
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int sub = threadIdx.x & 7;
+    const bool active = gid < (int64_t)S * vec_per_row;
     float4 acc = f4_zero();
-    int t = t0;
-    for (; t + 4 <= t1; t += 4) {
-        const float4 a = *reinterpret_cast<const float4*>(partials + (int64_t)t * C + c);
-        const float4 b = *reinterpret_cast<const float4*>(partials + (int64_t)(t + 1) * C + c);
-        const float4 d = *reinterpret_cast<const float4*>(partials + (int64_t)(t + 2) * C + c);
-        const float4 e = *reinterpret_cast<const float4*>(partials + (int64_t)(t + 3) * C + c);
-        acc = f4_add(f4_add(f4_add(f4_add(acc, a), b), d), e);
+    int n = 0, s = 0, c = 0;
+    if (active) {
+        s = (int)(gid / vec_per_row);
+        c = (int)(gid % vec_per_row) * 4;
+        n = seg_offsets[s + 1] - seg_offsets[s];
+        const int t0 = task_offsets[s], t1 = t0 + (n + run - 1) / run;
+        for (int t = t0 + sub; t < t1; t += 8)
+            acc = f4_add(acc, *reinterpret_cast<const float4*>(partials + (int64_t)t * C + c));
     }
-    for (; t < t1; ++t) acc = f4_add(acc, *reinterpret_cast<const float4*>(partials + (int64_t)t * C + c));
-    const int n = seg_offsets[s + 1] - seg_offsets[s];
-    *reinterpret_cast<float4*>(out + (int64_t)s * C + c) = f4_div(acc, (float)max(n, 1));
+    // fixed-order combine of the 8 sub-lane sums: ((0+1)+(2+3)) + ((4+5)+(6+7))
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        float4 other;
+        other.x = __shfl_xor_sync(kFull, acc.x, o);
+        other.y = __shfl_xor_sync(kFull, acc.y, o);
+        other.z = __shfl_xor_sync(kFull, acc.z, o);
+        other.w = __shfl_xor_sync(kFull, acc.w, o);
+        // both partners compute lo + hi in the same operand order -> identical bits
+        acc = (sub & o) ? f4_add(other, acc) : f4_add(acc, other);
+    }
+    if (active && sub == 0) *reinterpret_cast<float4*>(out + (int64_t)s * C + c) = f4_div(acc, (float)max(n, 1));
 }
 
 __global__ void finalize_kernel(float* __restrict__ sum, const int32_t* __restrict__ count, int64_t N, int C) {
@@ -494,7 +562,7 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
     p.partials = reinterpret_cast<float*>(ws);
     const int64_t n_tasks = pool ? max_tasks : ceil_div64(N, run);
     if (nchunks > 0)
-        project_kernel<<<(unsigned)ceil_div64(N, kProjWarps), kProjThreads, 0, stream>>>(p, masks, nchunks);
+        project_kernel<<<(unsigned)ceil_div64(N, kProjWarps * kProjPts), kProjThreads, 0, stream>>>(p, masks, nchunks);
     int rc;
     switch (fmap_dtype) {
         case SD3D_F32: rc = dispatch_gather<float>(p, masks, nchunks, n_tasks, variant, stream); break;
@@ -509,10 +577,10 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
 }
 
 extern "C" int sd3d_sp_combine(const void* partials, const int32_t* task_offsets, const int32_t* seg_offsets,
-                               int64_t S, int C, float* sp_out, void* stream_) {
+                               int64_t S, int C, int run, float* sp_out, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (S < 0 || C <= 0 || C % 4 != 0 || S >= (int64_t(1) << 30)) {
-        set_error("sd3d_sp_combine: bad shape S=%lld C=%d (C must be a multiple of 4)", (long long)S, C);
+    if (S < 0 || C <= 0 || C % 4 != 0 || S >= (int64_t(1) << 30) || run <= 0) {
+        set_error("sd3d_sp_combine: bad shape S=%lld C=%d run=%d (C must be a multiple of 4)", (long long)S, C, run);
         return SD3D_ERR_ARG;
     }
     if (S == 0) return SD3D_OK;
@@ -521,9 +589,9 @@ extern "C" int sd3d_sp_combine(const void* partials, const int32_t* task_offsets
         set_error("sd3d_sp_combine: null or misaligned buffer");
         return SD3D_ERR_ARG;
     }
-    const int64_t threads = S * (int64_t)(C / 4);
+    const int64_t threads = S * (int64_t)(C / 4) * 8;
     sp_combine_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(
-        reinterpret_cast<const float*>(partials), task_offsets, seg_offsets, (int32_t)S, C, sp_out);
+        reinterpret_cast<const float*>(partials), task_offsets, seg_offsets, (int32_t)S, C, run, sp_out);
     return check_launch("sd3d_sp_combine");
 }
 

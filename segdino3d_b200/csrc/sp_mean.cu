@@ -36,8 +36,9 @@ __global__ void __launch_bounds__(kMeanThreads)
         start = seg_offsets[task];
         end = seg_offsets[task + 1];
     } else {
-        if (task >= task_offsets[S]) return;  // tasks of the trash segment (>= task_offsets[S]) are skipped
+        if (task >= task_offsets[S + 1]) return;
         const int seg = task_seg[task];
+        if (seg >= S) return;  // runs of the trash segment (invalid ids) are not pooled
         start = (int64_t)seg_offsets[seg] + (task - task_offsets[seg]) * (int64_t)run;
         end = min(start + (int64_t)run, (int64_t)seg_offsets[seg + 1]);
     }
@@ -92,8 +93,9 @@ __global__ void __launch_bounds__(kMeanThreads)
         start = seg_offsets[task];
         end = seg_offsets[task + 1];
     } else {
-        if (task >= task_offsets[S]) return;
+        if (task >= task_offsets[S + 1]) return;
         const int seg = task_seg[task];
+        if (seg >= S) return;
         start = (int64_t)seg_offsets[seg] + (task - task_offsets[seg]) * (int64_t)run;
         end = min(start + (int64_t)run, (int64_t)seg_offsets[seg + 1]);
     }
@@ -112,16 +114,16 @@ __global__ void __launch_bounds__(kMeanThreads)
 
 // out[s,c] = (P[t0,c] + P[t0+1,c] + ...) / max(n_s,1), any C
 __global__ void sp_combine_rows_kernel(const float* __restrict__ partials, const int32_t* __restrict__ task_offsets,
-                                       const int32_t* __restrict__ seg_offsets, int32_t S, int C,
+                                       const int32_t* __restrict__ seg_offsets, int32_t S, int C, int run,
                                        float* __restrict__ out) {
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (int64_t)S * C) return;
     const int s = (int)(gid / C);
     const int c = (int)(gid % C);
-    const int t0 = task_offsets[s], t1 = task_offsets[s + 1];
+    const int n = seg_offsets[s + 1] - seg_offsets[s];
+    const int t0 = task_offsets[s], t1 = t0 + (n + run - 1) / run;
     float acc = 0.f;
     for (int t = t0; t < t1; ++t) acc = __fadd_rn(acc, partials[(int64_t)t * C + c]);
-    const int n = seg_offsets[s + 1] - seg_offsets[s];
     out[gid] = __fdiv_rn(acc, (float)max(n, 1));
 }
 
@@ -186,7 +188,7 @@ extern "C" int sd3d_sp_mean(const float* src, const int32_t* perm, const int32_t
     if (!exact) {
         const int64_t threads = S * (int64_t)C;
         sp_combine_rows_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(partials, task_offsets,
-                                                                                      seg_offsets, (int32_t)S, C, out);
+                                                                                      seg_offsets, (int32_t)S, C, run, out);
     }
     return check_launch("sd3d_sp_mean");
 }

@@ -52,7 +52,7 @@ class LiftOps:
     """Compute callables used by the exchange logic (CUDA kernels by default)."""
     lift_partial: Callable   # (xyz, K, w2c, depth, fmap, stride, tau, z_near, plan) -> (sum[N,C], count[N] int32)
     finalize: Callable       # (sum[N,C], count[N]) -> feat (may work in place)
-    plan: Callable           # (sp_ids, S) -> plan object
+    plan: Callable           # (sp_ids, S, xyz_or_None) -> plan object
     pool: Callable           # (feat[N,C], plan) -> sp_mean[S,C]
     seg_sizes: Callable      # (plan) -> int64 [S] points per superpoint
 
@@ -69,7 +69,8 @@ def cuda_ops(variant: int = 0, exact_pool: bool = False) -> LiftOps:
         s = plan.n_segments
         return (plan.seg_offsets[1:s + 1] - plan.seg_offsets[:s]).long()
 
-    return LiftOps(lift_partial=lift_partial, finalize=ops.lift_finalize, plan=ops.sp_sort,
+    return LiftOps(lift_partial=lift_partial, finalize=ops.lift_finalize,
+                   plan=lambda ids, s, xyz=None: ops.sp_sort(ids, s, xyz=xyz),
                    pool=lambda feat, plan: ops.sp_mean(feat, plan, exact=exact_pool), seg_sizes=seg_sizes)
 
 
@@ -85,7 +86,7 @@ def lift_view_sharded(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: torch
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = xyz.shape[0]
-    plan = ops.plan(sp_ids, n_superpoints)
+    plan = ops.plan(sp_ids, n_superpoints, xyz)
     part_sum, part_cnt = ops.lift_partial(xyz, K_local, w2c_local, depth_local, fmap_local, stride, tau, z_near, plan)
     if world == 1:
         feat = ops.finalize(part_sum, part_cnt)
@@ -114,7 +115,7 @@ def lift_view_sharded(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: torch
     feat_shard = ops.finalize(shard[:valid].contiguous(), cnt_shard)
     # pool the local rows (ids of other rows are parked: id -> S), turn means back into sums, reduce [S,C]
     local_ids = sp_ids[begin:end].contiguous()
-    local_plan = ops.plan(local_ids, n_superpoints)
+    local_plan = ops.plan(local_ids, n_superpoints, None)
     local_sizes = ops.seg_sizes(local_plan).to(feat_shard.dtype)
     sp_sum = ops.pool(feat_shard, local_plan) * local_sizes[:, None]
     sizes = local_sizes.clone()

@@ -55,6 +55,7 @@ def _need_cuda(name: str, t: torch.Tensor) -> None:
 class SuperpointPlan:
     """perm / seg_offsets (+ run table) for one concatenated batch of superpoint ids."""
     perm: torch.Tensor          # int32 [N]   point ids, superpoint by superpoint, ascending inside each
+    order: torch.Tensor         # int32 [N]   same segments, Morton-ordered inside each (== perm if not refined)
     seg_offsets: torch.Tensor   # int32 [S+2] superpoint s owns perm[seg_offsets[s]:seg_offsets[s+1]]; [S:S+2] = invalid ids
     task_offsets: torch.Tensor  # int32 [S+2]
     task_seg: torch.Tensor      # int32 [max_tasks]
@@ -64,8 +65,12 @@ class SuperpointPlan:
     max_tasks: int
 
 
-def sp_sort(index: torch.Tensor, n_segments: Optional[int] = None, run: int = DEFAULT_RUN) -> SuperpointPlan:
+def sp_sort(index: torch.Tensor, n_segments: Optional[int] = None, run: int = DEFAULT_RUN,
+            xyz: Optional[torch.Tensor] = None) -> SuperpointPlan:
     """Stable counting sort of point ids by superpoint id (replaces the implicit grouping of scatter_mean).
+
+    With ``xyz`` the plan also carries a spatially refined processing order for the lifting kernels
+    (Morton order inside each superpoint, superpoints laid out along the world Morton curve).
 
     ``n_segments=None`` -> ``int(index.max()) + 1`` exactly like torch_scatter (one host sync, the same
     ``.max().item()`` the reference does at spconvunet.py:371).
@@ -89,12 +94,21 @@ def sp_sort(index: torch.Tensor, n_segments: Optional[int] = None, run: int = DE
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         check(lib.sd3d_sp_sort(_ptr(index), n, s, _ptr(perm), _ptr(seg_offsets), _ptr(ws), ws_bytes, _stream()),
               "sd3d_sp_sort")
+        order, anchor = perm, None
+        if xyz is not None:
+            _need_cuda("xyz", xyz)
+            if xyz.dtype != torch.float32 or tuple(xyz.shape) != (n, 3):
+                raise ValueError("xyz must be float32 [N,3]")
+            order = torch.empty(n, dtype=torch.int32, device=dev)
+            anchor = torch.empty(s + 1, dtype=torch.int32, device=dev)
+            check(lib.sd3d_sp_refine(_ptr(xyz.contiguous()), _ptr(perm), _ptr(seg_offsets), n, s, _ptr(order),
+                                     _ptr(anchor), _stream()), "sd3d_sp_refine")
         max_tasks = int(lib.sd3d_sp_max_tasks(n, s, run))
         task_offsets = torch.empty(s + 2, dtype=torch.int32, device=dev)
         task_seg = torch.empty(max(max_tasks, 1), dtype=torch.int32, device=dev)
-        check(lib.sd3d_sp_tasks(_ptr(seg_offsets), s, run, _ptr(task_offsets), _ptr(task_seg), max_tasks, _stream()),
-              "sd3d_sp_tasks")
-    return SuperpointPlan(perm, seg_offsets, task_offsets, task_seg, n, s, run, max_tasks)
+        check(lib.sd3d_sp_tasks(_ptr(seg_offsets), _ptr(anchor), s, run, _ptr(task_offsets), _ptr(task_seg), max_tasks,
+                                _stream()), "sd3d_sp_tasks")
+    return SuperpointPlan(perm, order, seg_offsets, task_offsets, task_seg, n, s, run, max_tasks)
 
 
 def sp_mean(src: torch.Tensor, plan: SuperpointPlan, exact: bool = True,
@@ -257,7 +271,7 @@ def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Ten
         check(lib.sd3d_lift(_ptr(xyz), n, _ptr(K), _ptr(w2c), v, vb, ve, _ptr(depth), _DEPTH_CODE[depth.dtype], hd, wd,
                             _ptr(fmap), _FMAP_CODE[fmap.dtype], hf, wf, c, float(stride), float(tau), float(z_near),
                             1 if accumulate_into is not None else 0, 1 if finalize else 0,
-                            _ptr(plan.perm) if plan is not None else None, _ptr(feat), _ptr(count), _ptr(pix),
+                            _ptr(plan.order) if plan is not None else None, _ptr(feat), _ptr(count), _ptr(pix),
                             _ptr(vis), _ptr(plan.seg_offsets) if plan is not None else None, s,
                             _ptr(plan.task_offsets) if plan is not None else None,
                             _ptr(plan.task_seg) if plan is not None else None,
@@ -266,8 +280,8 @@ def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Ten
         if events is not None:
             events[1].record()
         if pool:
-            check(lib.sd3d_sp_combine(_ptr(ws), _ptr(plan.task_offsets), _ptr(plan.seg_offsets), s, c, _ptr(sp_out),
-                                      _stream()), "sd3d_sp_combine")
+            check(lib.sd3d_sp_combine(_ptr(ws), _ptr(plan.task_offsets), _ptr(plan.seg_offsets), s, c, plan.run,
+                                      _ptr(sp_out), _stream()), "sd3d_sp_combine")
     return {"feat": feat, "count": count, "pix_idx": pix, "vis": vis, "sp_feat": sp_out}
 
 
@@ -318,7 +332,7 @@ def lift_and_pool(xyz, K, pose_w2c, depth, fmap, sp_ids: torch.Tensor, n_superpo
                   run: int = DEFAULT_RUN, variant: int = 0):
     """The whole hot path for one scene: sort by superpoint -> fused lift + mean + superpoint pooling.
     Returns (points_2dfeats [N,C], count [N], sp_feats [S,C], plan)."""
-    plan = sp_sort(sp_ids, n_superpoints, run=run)
+    plan = sp_sort(sp_ids, n_superpoints, run=run, xyz=xyz)
     r = lift(xyz, K, pose_w2c, depth, fmap, stride, tau=tau, z_near=z_near, plan=plan, pool=True, variant=variant)
     return r["feat"], r["count"], r["sp_feat"], plan
 

@@ -100,7 +100,7 @@ class PointFeatureLifter:
         for pts, tgt, vw in zip(samples, targets, views):
             xyz = pts[:, :3].contiguous()
             sp = tgt["extra_features"].get("super_point_masks")
-            plan = ops.sp_sort(sp) if sp is not None else None
+            plan = ops.sp_sort(sp, xyz=xyz) if sp is not None else None
             feats = ops.lift_features(xyz, vw["K"], vw["w2c"], vw["depth"], vw["fmaps"], tau=self.tau,
                                       z_near=self.z_near, strides=vw.get("strides"), order=plan)
             tgt["extra_features"]["points_2dfeats"] = feats[0] if len(feats) == 1 else ops.scale_mean(feats)

@@ -25,7 +25,7 @@ def _oracle_ops():
     from segdino3d_b200.dist import LiftOps
 
     class Plan:
-        def __init__(self, ids, s):
+        def __init__(self, ids, s, xyz=None):
             self.ids, self.s = ids, s
 
     def lift_partial(xyz, K, w2c, depth, fmap, stride, tau, z_near, plan):

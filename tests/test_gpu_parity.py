@@ -53,6 +53,42 @@ def test_sp_sort_bit_exact(n, s):
     assert torch.equal(seg_of_task, torch.repeat_interleave(torch.arange(s + 1), torch.cat([want_tasks, t_off[s + 1:s + 2].long() - t_off[s:s + 1].long()])))
 
 
+def test_sp_refine_permutes_inside_segments_only():
+    """The Morton refinement may only reorder points inside their superpoint; the run table may be laid out
+    in any superpoint order but must tile every superpoint with consecutive runs."""
+    sc = make_scene(n_points=30_000, n_views=1, hd=24, wd=32, stride=8, channels=4, seed=17, sp_target=120,
+                    adversarial_sp=True)
+    s = sc.n_superpoints
+    plan = sd.sp_sort(sc.sp_ids.to(DEV), s, xyz=sc.xyz.to(DEV))
+    perm, offs = so.sp_sort_oracle(sc.sp_ids, s)
+    assert torch.equal(plan.perm.cpu(), perm)
+    order = plan.order.cpu().long()
+    assert torch.equal(torch.sort(order).values, torch.arange(30_000))
+    assert torch.equal(sc.sp_ids[order], sc.sp_ids[perm.long()])       # same superpoint at every sorted position
+    # spatial coherence: consecutive points of the refined order are much closer than in id order
+    big = int((offs[1:] - offs[:-1]).argmax())
+    seg_r = order[offs[big]: offs[big + 1]]
+    seg_p = perm[offs[big]: offs[big + 1]].long()
+    step_r = (sc.xyz[seg_r][1:] - sc.xyz[seg_r][:-1]).norm(dim=1).mean()
+    step_p = (sc.xyz[seg_p][1:] - sc.xyz[seg_p][:-1]).norm(dim=1).mean()
+    assert float(step_r) < 0.5 * float(step_p)
+    t_off, t_seg = plan.task_offsets.cpu().long(), plan.task_seg.cpu().long()
+    sizes = torch.cat([offs[1:] - offs[:-1], torch.tensor([30_000 - int(offs[-1])])]).long()
+    n_tasks = (sizes + plan.run - 1) // plan.run
+    assert int(t_off[s + 1]) == int(n_tasks.sum())
+    covered = torch.zeros(int(n_tasks.sum()), dtype=torch.long)
+    for seg in range(s + 1):
+        t0 = int(t_off[seg])
+        assert (t_seg[t0: t0 + int(n_tasks[seg])] == seg).all()
+        covered[t0: t0 + int(n_tasks[seg])] += 1
+    assert (covered == 1).all()
+    # pooled results do not depend on the refinement
+    src = torch.randn(30_000, 64, generator=torch.Generator().manual_seed(0))
+    want = so.scatter_mean_oracle(src, sc.sp_ids, dim=0, dim_size=s)
+    assert torch.equal(sd.sp_mean(src.to(DEV), plan, exact=True).cpu(), want)
+    assert rel_row_err(sd.sp_mean(src.to(DEV), plan, exact=False), want, floor=1.0) <= 1e-5
+
+
 def test_sp_sort_invalid_ids_are_parked():
     idx = torch.tensor([3, -1, 0, 99, 3, 0, 5, 2])
     plan = sd.sp_sort(idx.to(DEV), 5)
