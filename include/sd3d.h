@@ -61,15 +61,17 @@ int sd3d_sp_sort(const int64_t* idx, int64_t N, int64_t S, int32_t* perm, int32_
  * (segment S = the invalid-id points, which are lifted but never pooled); task_offsets[S+1] = task count.
  * max_tasks = sd3d_sp_max_tasks(N,S,run) is the size the caller must give task_seg. */
 int64_t sd3d_sp_max_tasks(int64_t N, int64_t S, int run);
-int sd3d_sp_tasks(const int32_t* seg_offsets, const uint32_t* anchor /*nullable*/, int64_t S, int run,
-                  int32_t* task_offsets, int32_t* task_seg, int64_t max_tasks, void* stream);
+int sd3d_sp_tasks(const int32_t* seg_offsets, int64_t S, int run, int32_t* task_offsets, int32_t* task_seg,
+                  int64_t max_tasks, void* stream);
 
-/* Spatial refinement of the processing order (cache locality only -- results never depend on it):
- * order[N] = perm with the points of every superpoint re-ordered along a Morton curve; anchor[S+1] = one
- * world-grid Morton key per superpoint, which sd3d_sp_tasks uses to lay the runs out along the same curve.
- * xyz[N,3] f32 as given to sd3d_lift. No reference counterpart (the reference gathers nothing). */
-int sd3d_sp_refine(const float* xyz, const int32_t* perm, const int32_t* seg_offsets, int64_t N, int64_t S,
-                   int32_t* order, uint32_t* anchor, void* stream);
+/* The whole plan of the lifting path in one call: sd3d_sp_sort + spatial refinement + run table.
+ * order[N] = perm with the points of every superpoint re-ordered along a Morton curve (world grid of
+ * `cell` metres, e.g. 0.08), and the runs of task_seg laid out superpoint by superpoint along the world
+ * Morton curve -- cache locality only, results of sd3d_lift never depend on it. xyz[N,3] f32 as given to
+ * sd3d_lift. ws: sd3d_sp_sort_workspace_bytes(N,S). No reference counterpart (the reference gathers nothing). */
+int sd3d_sp_plan(const int64_t* idx, const float* xyz, int64_t N, int64_t S, int run, float cell, int32_t* perm,
+                 int32_t* order, int32_t* seg_offsets, int32_t* task_offsets, int32_t* task_seg, int64_t max_tasks,
+                 void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * a-4: out[s,:] = sum_{p in s} src[p,:] / max(|s|,1)    == scatter_mean(src, idx, dim=0)

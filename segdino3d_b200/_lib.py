@@ -23,8 +23,9 @@ SYMBOLS = {
     "sd3d_sp_sort_workspace_bytes": (c_size_t, [c_int64, c_int64]),
     "sd3d_sp_sort": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sd3d_sp_max_tasks": (c_int64, [c_int64, c_int64, c_int]),
-    "sd3d_sp_tasks": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
-    "sd3d_sp_refine": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p]),
+    "sd3d_sp_tasks": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
+    "sd3d_sp_plan": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_int64, c_void_p, c_size_t, c_void_p]),
     "sd3d_sp_mean": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p,
                              c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
     "sd3d_lift_workspace_bytes": (c_size_t, [c_int64, c_int, c_int, c_int64]),

@@ -1,16 +1,22 @@
-// sp_sort.cu -- stable counting/radix sort of points by superpoint id, and the run ("task") table.
+// sp_sort.cu -- the superpoint "plan": stable sort of points by superpoint id, spatial refinement of the
+// processing order, and the run ("task") table.
 //
-// Replaces the grouping that torch_scatter.scatter_mean performs with one global atomicAdd per
-// element (reference call sites: segdino3d/models/backbone/spconvunet.py:390,392; minkunet.py:639,641).
-// Sorting once turns the pooling into segmented reductions with no atomics on fp32 data, and gives the
-// lifting kernel a spatially coherent processing order (superpoints are compact in space).
+// Replaces the grouping that torch_scatter.scatter_mean performs with one global atomicAdd per element
+// (reference call sites: segdino3d/models/backbone/spconvunet.py:390,392; minkunet.py:639,641). Sorting
+// once turns the pooling into segmented reductions with no atomics on fp32 data, and gives the lifting
+// kernels a spatially coherent processing order.
 //
-// Integer-only work, bit-exact by construction: perm is the unique stable permutation.
+// Integer-only work, bit-exact by construction: perm is the unique stable permutation; `order` is a
+// deterministic function of (ids, xyz).
 //
-// Algorithm: LSD radix passes over ceil(log2(S+1)) key bits, <=10 bits per pass (one pass for S<1024).
-//   pass = hist (per-block digit histogram, smem int atomics)
-//        -> scan (single CTA exclusive scan of the bin-major [bins][blocks] matrix = global bases)
-//        -> scatter (per-warp contiguous sub-chunks; __match_any_sync ranks keep equal keys in input order)
+// Pipeline (all kernels tiny and latency-bound at ScanNet sizes, so the count of launches is what matters):
+//   radix pass = hist (per-block digit histogram, smem int atomics)
+//              -> scan (ONE CTA, whole bin-major [bins][blocks] matrix staged in shared memory)
+//              -> scatter (per-warp contiguous sub-chunks; __match_any_sync ranks keep equal keys in input
+//                 order; the last pass also emits a 9-bit Morton cell key per sorted point)
+//   one pass for S < 1024, ceil(log2(S+1)/10) passes otherwise (+ a boundary-search kernel).
+//   refine = per-superpoint stable counting sort by the cell key (one CTA per superpoint, 512 bins)
+//   tasks  = superpoints ranked along the world Morton curve, ceil(n_s/run) runs each (ONE CTA).
 // Keys outside [0,S) are mapped to the extra key S ("trash"), which sorts last.
 #include "common.cuh"
 
@@ -20,6 +26,7 @@ constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kMaxDigitBits = 10;
 constexpr int kMaxSortBlocks = 256;
+constexpr int kScanCap = 48 * 1024;  // ints of the [bins][blocks] matrix that fit the scan CTA's smem (192 KB)
 
 struct SortGeom {
     int key_bits, passes, bits_per_pass, items_per_block, nb;
@@ -32,7 +39,10 @@ static SortGeom sort_geom(int64_t N, int64_t S) {
     g.key_bits = kb;
     g.passes = (kb + kMaxDigitBits - 1) / kMaxDigitBits;
     g.bits_per_pass = (kb + g.passes - 1) / g.passes;
-    int64_t t = ceil_div64(N > 0 ? N : 1, kMaxSortBlocks);
+    const int max_bins = 1 << (g.passes == 1 ? kb : g.bits_per_pass);
+    int nb_cap = kScanCap / max_bins;
+    if (nb_cap > kMaxSortBlocks) nb_cap = kMaxSortBlocks;
+    int64_t t = ceil_div64(N > 0 ? N : 1, nb_cap);
     t = ceil_div64(t, kSortThreads) * kSortThreads;
     if (t < 1024) t = 1024;
     g.items_per_block = (int)t;
@@ -41,6 +51,26 @@ static SortGeom sort_geom(int64_t N, int64_t S) {
 }
 
 __device__ __forceinline__ int32_t clamp_key(int64_t id, int32_t S) { return (id < 0 || id >= S) ? S : (int32_t)id; }
+
+// 10-bit-per-axis Morton code
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v &= 0x3FFu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t morton30(uint32_t x, uint32_t y, uint32_t z) {
+    return spread10(x) | (spread10(y) << 1) | (spread10(z) << 2);
+}
+// position of a point inside its (8 cells)^3 block of the world grid, as a 9-bit Morton code. Points of one
+// superpoint that fall into the same block are ordered along the curve; a superpoint straddling a block
+// border is ordered piecewise -- good enough for cache locality, and it needs no bounding boxes.
+__device__ __forceinline__ uint32_t cell_key9(float x, float y, float z, float inv_cell) {
+    const int cx = (int)floorf(x * inv_cell) & 7, cy = (int)floorf(y * inv_cell) & 7, cz = (int)floorf(z * inv_cell) & 7;
+    return morton30(cx, cy, cz) & 0x1FFu;
+}
 
 template <bool FIRST>
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const int64_t* __restrict__ idx,
@@ -61,43 +91,39 @@ __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const int64_t*
     for (int i = threadIdx.x; i < bins; i += blockDim.x) hist[(int64_t)i * nb + blockIdx.x] = s_hist[i];
 }
 
-// In-place exclusive scan of the bin-major matrix hist[bins][nb] (nb <= 256) by ONE CTA of 1024 threads:
-// each warp scans whole rows (8 values per lane, all loads of a row in flight at once), the 32 warps'
-// row totals are scanned through shared memory, then the row bases are added. Optionally emits
-// seg_offsets[s] = scanned[s*nb] for s in [0,S] (valid when a single pass covers all key bits).
+// In-place exclusive scan of the bin-major matrix hist[bins][nb] (bins*nb <= kScanCap) by ONE CTA: the whole
+// matrix is staged in shared memory with coalesced loads that are all in flight at once (the kernel is
+// latency-bound), rows are scanned by warps, row totals by the CTA. Optionally emits seg_offsets[s] = global
+// start of key s for s in [0,S] (valid when a single pass covers all key bits).
 __global__ void __launch_bounds__(1024) radix_scan_kernel(int32_t* __restrict__ hist, int bins, int nb,
                                                           int32_t* __restrict__ seg_offsets, int32_t S, int64_t N) {
+    extern __shared__ int32_t s_mat[];  // [bins*nb]
     __shared__ int32_t s_rowbase[1 << kMaxDigitBits];
     __shared__ int32_t s_warp[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int kPer = kMaxSortBlocks / 32;  // 8 values per lane cover nb <= 256
-    // pass 1: row-local exclusive scan in registers, row totals to smem
+    const int total = bins * nb;
+    for (int i = tid; i < total; i += 1024) s_mat[i] = hist[i];
+    __syncthreads();
+    // rows: exclusive scan of each row in place, row total to s_rowbase
     for (int row = warp; row < bins; row += 32) {
-        int32_t v[kPer];
-        int32_t tsum = 0;
+        int32_t* r = s_mat + row * nb;
+        int32_t carry = 0;
+        for (int c0 = 0; c0 < nb; c0 += 32) {
+            const int col = c0 + lane;
+            const int32_t v = col < nb ? r[col] : 0;
+            int32_t inc = v;
 #pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            const int col = lane * kPer + k;
-            v[k] = col < nb ? hist[(int64_t)row * nb + col] : 0;
-            tsum += v[k];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t n = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += n;
+            }
+            if (col < nb) r[col] = carry + inc - v;
+            carry += __shfl_sync(kFull, inc, 31);
         }
-        int32_t inc = tsum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int32_t n = __shfl_up_sync(kFull, inc, o);
-            if (lane >= o) inc += n;
-        }
-        int32_t excl = inc - tsum;
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            const int col = lane * kPer + k;
-            if (col < nb) hist[(int64_t)row * nb + col] = excl;
-            excl += v[k];
-        }
-        if (lane == 31) s_rowbase[row] = inc;  // row total
+        if (lane == 0) s_rowbase[row] = carry;
     }
     __syncthreads();
-    // pass 2: exclusive scan of the row totals (bins <= 1024 = one value per thread)
+    // exclusive scan of the row totals (bins <= 1024 = one value per thread)
     {
         const int32_t t = tid < bins ? s_rowbase[tid] : 0;
         int32_t inc = t;
@@ -121,17 +147,9 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(int32_t* __restrict__ 
         if (tid < bins) s_rowbase[tid] = inc - t + (warp > 0 ? s_warp[warp - 1] : 0);
     }
     __syncthreads();
-    // pass 3: add the row bases
-    for (int row = warp; row < bins; row += 32) {
-        const int32_t base = s_rowbase[row];
-#pragma unroll
-        for (int k = 0; k < kPer; ++k) {
-            const int col = lane * kPer + k;
-            if (col < nb) hist[(int64_t)row * nb + col] += base;
-        }
-    }
+    for (int i = tid; i < total; i += 1024) hist[i] = s_mat[i] + s_rowbase[i / nb];
     if (seg_offsets != nullptr) {
-        for (int s = tid; s <= S; s += blockDim.x) seg_offsets[s] = s_rowbase[s];
+        for (int s = tid; s <= S; s += 1024) seg_offsets[s] = s_rowbase[s];
         if (tid == 0) seg_offsets[S + 1] = (int32_t)N;  // end of the trash segment
     }
 }
@@ -141,7 +159,8 @@ __global__ void __launch_bounds__(kSortThreads)
     radix_scatter_kernel(const int64_t* __restrict__ idx, const int32_t* __restrict__ keys_in,
                          const int32_t* __restrict__ vals_in, int64_t N, int32_t S, int shift, int bits,
                          int items_per_block, int nb, const int32_t* __restrict__ base, int32_t* __restrict__ keys_out,
-                         int32_t* __restrict__ vals_out) {
+                         int32_t* __restrict__ vals_out, const float* __restrict__ xyz, float inv_cell,
+                         uint16_t* __restrict__ cell_out) {
     extern __shared__ int32_t s_cnt[];  // [kSortWarps][bins]
     const int bins = 1 << bits;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -187,8 +206,14 @@ __global__ void __launch_bounds__(kSortThreads)
         if (active && rank == 0) my_cnt[digit] += __popc(peers);
         __syncwarp();
         if (active) {
+            const int32_t val = FIRST ? (int32_t)i : vals_in[i];
             if (keys_out != nullptr) keys_out[dst] = key;
-            vals_out[dst] = FIRST ? (int32_t)i : vals_in[i];
+            vals_out[dst] = val;
+            if (cell_out != nullptr) {
+                const float x = __ldg(xyz + 3 * (int64_t)val), y = __ldg(xyz + 3 * (int64_t)val + 1),
+                            z = __ldg(xyz + 3 * (int64_t)val + 2);
+                cell_out[dst] = (uint16_t)cell_key9(x, y, z, inv_cell);
+            }
         }
     }
 }
@@ -204,17 +229,88 @@ __global__ void seg_bounds_kernel(const int32_t* __restrict__ sorted_keys, int64
     if (i == N) seg_offsets[S + 1] = (int32_t)N;  // end of the trash segment
 }
 
-// 10-bit-per-axis Morton code
-__device__ __forceinline__ uint32_t spread10(uint32_t v) {
-    v &= 0x3FFu;
-    v = (v | (v << 16)) & 0x030000FFu;
-    v = (v | (v << 8)) & 0x0300F00Fu;
-    v = (v | (v << 4)) & 0x030C30C3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-__device__ __forceinline__ uint32_t morton30(uint32_t x, uint32_t y, uint32_t z) {
-    return spread10(x) | (spread10(y) << 1) | (spread10(z) << 2);
+// Spatial refinement: inside every superpoint the points are re-ordered by their 9-bit Morton cell key with a
+// stable counting sort (one CTA per superpoint; same three phases as radix_scatter_kernel), so that the points
+// one CTA lifts together project to neighbouring pixels. `order` is a permutation of `perm` inside each
+// segment; lifting results do not depend on it (only cache behaviour does). Also emits one world-grid Morton
+// key per superpoint (`anchor`, 0.25 m cells) used to walk the superpoints in a spatially coherent order.
+constexpr int kRefineBins = 512;
+
+__global__ void __launch_bounds__(kSortThreads)
+    sp_refine_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ perm,
+                     const uint16_t* __restrict__ cell, const int32_t* __restrict__ seg_offsets,
+                     int32_t* __restrict__ order, uint32_t* __restrict__ anchor) {
+    __shared__ int32_t s_cnt[kSortWarps][kRefineBins];
+    __shared__ int32_t s_tot[kRefineBins];
+    __shared__ int32_t s_warp[kSortWarps];
+    const int seg = blockIdx.x;
+    const int beg = seg_offsets[seg], end = seg_offsets[seg + 1];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    if (end <= beg) {
+        if (threadIdx.x == 0) anchor[seg] = 0x7FFFFFFFu;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        const int32_t p0 = perm[beg];
+        const int gx = min(max((int)floorf(__ldg(xyz + 3 * (int64_t)p0) * 4.0f) + 512, 0), 1023);
+        const int gy = min(max((int)floorf(__ldg(xyz + 3 * (int64_t)p0 + 1) * 4.0f) + 512, 0), 1023);
+        const int gz = min(max((int)floorf(__ldg(xyz + 3 * (int64_t)p0 + 2) * 4.0f) + 512, 0), 1023);
+        anchor[seg] = morton30(gx, gy, gz);
+    }
+    for (int i = threadIdx.x; i < kSortWarps * kRefineBins; i += blockDim.x) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    const int n = end - beg;
+    const int per_warp = ((n + kSortWarps - 1) / kSortWarps + 31) / 32 * 32;
+    const int wbeg = min(beg + warp * per_warp, end), wend = min(wbeg + per_warp, end);
+    for (int i = wbeg + lane; i < wend; i += 32) atomicAdd(&s_cnt[warp][cell[i]], 1);
+    __syncthreads();
+    // bin totals -> exclusive scan over bins (2 bins per thread) -> running offsets per (warp, bin)
+    {
+        const int b0 = threadIdx.x * 2;
+        int32_t t0 = 0, t1 = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            t0 += s_cnt[w][b0];
+            t1 += s_cnt[w][b0 + 1];
+        }
+        int32_t inc = t0 + t1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t v = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += v;
+        }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        int32_t wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+        const int32_t excl = wbase + inc - (t0 + t1);
+        s_tot[b0] = excl;
+        s_tot[b0 + 1] = excl + t0;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kRefineBins; b += blockDim.x) {
+        int32_t run = beg + s_tot[b];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const int32_t c = s_cnt[w][b];
+            s_cnt[w][b] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int i0 = wbeg; i0 < wend; i0 += 32) {
+        const int i = i0 + lane;
+        const bool active = i < wend;
+        const int digit = active ? (int)cell[i] : kRefineBins;
+        const unsigned peers = __match_any_sync(kFull, digit);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        int32_t dst = 0;
+        if (active) dst = s_cnt[warp][digit] + rank;
+        __syncwarp();
+        if (active && rank == 0) s_cnt[warp][digit] += __popc(peers);
+        __syncwarp();
+        if (active) order[dst] = perm[i];
+    }
 }
 
 // in-smem bitonic sort of n2 (power of two) 64-bit items (key << 32 | value) by the whole CTA
@@ -237,103 +333,13 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* items, int n2) {
     }
 }
 
-// Spatial refinement of the processing order: inside every superpoint the points are re-ordered along a
-// Morton curve (chunks of <= kRefineChunk points, keys relative to the chunk's bounding box), so that the
-// points one CTA lifts together project to neighbouring pixels. `order` is a permutation of `perm` inside
-// each segment; results of the lifting do not depend on it (only cache behaviour does). Also emits one
-// world-grid Morton key per superpoint (`anchor`), used to walk the superpoints in a spatially coherent order.
-// Integer/compare-only work: deterministic.
-constexpr int kRefineChunk = 2048;
-constexpr int kRefineThreads = 256;
-
-__global__ void __launch_bounds__(kRefineThreads)
-    sp_refine_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ perm,
-                     const int32_t* __restrict__ seg_offsets, int32_t* __restrict__ order,
-                     uint32_t* __restrict__ anchor) {
-    __shared__ uint64_t s_items[kRefineChunk];
-    __shared__ float s_red[6][kRefineThreads / 32];
-    __shared__ float s_box[6];
-    const int seg = blockIdx.x;
-    const int beg = seg_offsets[seg], end = seg_offsets[seg + 1];
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    if (end <= beg) {
-        if (threadIdx.x == 0) anchor[seg] = 0x7FFFFFFFu;
-        return;
-    }
-    for (int c0 = beg; c0 < end; c0 += kRefineChunk) {
-        const int n = min(kRefineChunk, end - c0);
-        float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int32_t pid = perm[c0 + i];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) {
-                const float v = __ldg(xyz + 3 * (int64_t)pid + a);
-                if (v == v) {  // NaNs do not move the box
-                    lo[a] = fminf(lo[a], v);
-                    hi[a] = fmaxf(hi[a], v);
-                }
-            }
-        }
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                lo[a] = fminf(lo[a], __shfl_xor_sync(kFull, lo[a], o));
-                hi[a] = fmaxf(hi[a], __shfl_xor_sync(kFull, hi[a], o));
-            }
-            if (lane == 0) {
-                s_red[a][warp] = lo[a];
-                s_red[3 + a][warp] = hi[a];
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x < 6) {
-            float v = s_red[threadIdx.x][0];
-            for (int w = 1; w < kRefineThreads / 32; ++w)
-                v = threadIdx.x < 3 ? fminf(v, s_red[threadIdx.x][w]) : fmaxf(v, s_red[threadIdx.x][w]);
-            s_box[threadIdx.x] = v;
-        }
-        __syncthreads();
-        const float bx = s_box[0], by = s_box[1], bz = s_box[2];
-        const float ext = fmaxf(fmaxf(s_box[3] - bx, s_box[4] - by), fmaxf(s_box[5] - bz, 1e-6f));
-        const float scale = 1023.0f / ext;
-        if (c0 == beg && threadIdx.x == 0) {
-            // world-grid key of the box centre: 0.25 m cells, grid origin at -128 m
-            const float cx = 0.5f * (s_box[0] + s_box[3]), cy = 0.5f * (s_box[1] + s_box[4]),
-                        cz = 0.5f * (s_box[2] + s_box[5]);
-            const int gx = min(max((int)floorf(cx * 4.0f) + 512, 0), 1023);
-            const int gy = min(max((int)floorf(cy * 4.0f) + 512, 0), 1023);
-            const int gz = min(max((int)floorf(cz * 4.0f) + 512, 0), 1023);
-            anchor[seg] = morton30(gx, gy, gz);
-        }
-        int n2 = 1;
-        while (n2 < n) n2 <<= 1;
-        for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-            uint64_t item = ~uint64_t(0);  // padding sorts last
-            if (i < n) {
-                const int32_t pid = perm[c0 + i];
-                const float x = __ldg(xyz + 3 * (int64_t)pid), y = __ldg(xyz + 3 * (int64_t)pid + 1),
-                            z = __ldg(xyz + 3 * (int64_t)pid + 2);
-                const int qx = min(max((int)((x - bx) * scale), 0), 1023);
-                const int qy = min(max((int)((y - by) * scale), 0), 1023);
-                const int qz = min(max((int)((z - bz) * scale), 0), 1023);
-                item = ((uint64_t)morton30(qx, qy, qz) << 32) | (uint32_t)pid;
-            }
-            s_items[i] = item;
-        }
-        __syncthreads();
-        bitonic_sort_smem(s_items, n2);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) order[c0 + i] = (int32_t)(s_items[i] & 0xFFFFFFFFu);
-        __syncthreads();
-    }
-}
-
 // Task table. Segment s (n_s points) gets ceil(n_s/run) consecutive tasks starting at task_offsets[s];
 // task_seg[t] = segment of task t; task_offsets[nseg] = total number of tasks (nseg counts the trash
 // segment). With `anchor` the segments are laid out along the world Morton curve (spatially coherent
-// CTAs run at the same time -> the feature-map regions they touch stay in L2), else in id order.
-// ONE CTA of 1024 threads; ordering is skipped when nseg exceeds the in-smem sort capacity.
+// CTAs run at the same time -> the feature-map regions they touch stay in L1/L2), else in id order.
+// ONE CTA of 1024 threads; nseg <= 1024: rank by counting (no barriers); <= 8192: bitonic; else id order.
 constexpr int kMaxOrderedSegs = 8192;
+constexpr int kMaxRankedSegs = 1024;
 
 __global__ void __launch_bounds__(1024) sp_tasks_kernel(const int32_t* __restrict__ seg_offsets,
                                                         const uint32_t* __restrict__ anchor, int32_t nseg, int run,
@@ -345,16 +351,29 @@ __global__ void __launch_bounds__(1024) sp_tasks_kernel(const int32_t* __restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool ordered = anchor != nullptr && nseg <= kMaxOrderedSegs;
     if (ordered) {
-        int n2 = 1;
-        while (n2 < nseg) n2 <<= 1;
-        for (int i = tid; i < n2; i += blockDim.x) {
-            uint64_t item = ~uint64_t(0);
-            // the trash segment (last) keeps the largest real key so that it stays at the end
-            if (i < nseg) item = ((uint64_t)(i == nseg - 1 ? 0xFFFFFFFEu : anchor[i]) << 32) | (uint32_t)i;
-            s_sorted[i] = item;
+        // the trash segment (last) gets the largest key so that it stays at the end
+        if (nseg <= kMaxRankedSegs) {
+            uint64_t mine = ~uint64_t(0);
+            if (tid < nseg) mine = ((uint64_t)(tid == nseg - 1 ? 0xFFFFFFFEu : anchor[tid]) << 32) | (uint32_t)tid;
+            s_sorted[kMaxRankedSegs + tid] = mine;  // staging half
+            __syncthreads();
+            if (tid < nseg) {
+                int rank = 0;
+                for (int t = 0; t < nseg; ++t) rank += s_sorted[kMaxRankedSegs + t] < mine ? 1 : 0;  // keys are distinct
+                s_sorted[rank] = mine;
+            }
+            __syncthreads();
+        } else {
+            int n2 = 1;
+            while (n2 < nseg) n2 <<= 1;
+            for (int i = tid; i < n2; i += blockDim.x) {
+                uint64_t item = ~uint64_t(0);
+                if (i < nseg) item = ((uint64_t)(i == nseg - 1 ? 0xFFFFFFFEu : anchor[i]) << 32) | (uint32_t)i;
+                s_sorted[i] = item;
+            }
+            __syncthreads();
+            bitonic_sort_smem(s_sorted, n2);
         }
-        __syncthreads();
-        bitonic_sort_smem(s_sorted, n2);
     }
     if (tid == 0) s_carry = 0;
     __syncthreads();
@@ -398,40 +417,54 @@ __global__ void __launch_bounds__(1024) sp_tasks_kernel(const int32_t* __restric
     if (tid == 0) task_offsets[nseg] = s_carry;
 }
 
-}  // namespace sd3d
+static size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-using namespace sd3d;
+struct SortWs {
+    int32_t* hist;
+    int32_t* bufs;      // 4 * N ints (ping-pong keys / values of multi-pass sorts)
+    uint16_t* cell;     // N
+    uint32_t* anchor;   // S + 1
+};
 
-extern "C" size_t sd3d_sp_sort_workspace_bytes(int64_t N, int64_t S) {
-    (void)S;
-    if (N < 0) N = 0;
-    return (size_t)(1 << kMaxDigitBits) * kMaxSortBlocks * sizeof(int32_t) + 4 * (size_t)N * sizeof(int32_t) + 1024;
+static size_t sort_ws_layout(int64_t N, int64_t S, void* ws, SortWs* out) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = ws ? static_cast<uint8_t*>(ws) + off : nullptr;
+        off += align_up_sz(bytes, 256);
+        return p;
+    };
+    SortWs w;
+    w.hist = static_cast<int32_t*>(take((size_t)kScanCap * sizeof(int32_t)));
+    w.bufs = static_cast<int32_t*>(take(4 * (size_t)(N > 0 ? N : 0) * sizeof(int32_t)));
+    w.cell = static_cast<uint16_t*>(take((size_t)(N > 0 ? N : 0) * sizeof(uint16_t)));
+    w.anchor = static_cast<uint32_t*>(take((size_t)(S + 1) * sizeof(uint32_t)));
+    if (out) *out = w;
+    return off + 256;
 }
 
-extern "C" int sd3d_sp_sort(const int64_t* idx, int64_t N, int64_t S, int32_t* perm, int32_t* seg_offsets, void* ws,
-                            size_t ws_bytes, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (N < 0 || S < 0 || N >= (int64_t(1) << 31) - 64 || S >= (int64_t(1) << 30)) {
-        set_error("sd3d_sp_sort: N=%lld S=%lld out of range", (long long)N, (long long)S);
-        return SD3D_ERR_ARG;
+static int set_smem_attr_once(const void* fn, int bytes, bool* done, const char* what) {
+    if (*done) return SD3D_OK;
+    const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+        return SD3D_ERR_CUDA;
     }
-    if (seg_offsets == nullptr || (N > 0 && (idx == nullptr || perm == nullptr)) || ws == nullptr ||
-        ws_bytes < sd3d_sp_sort_workspace_bytes(N, S)) {
-        set_error("sd3d_sp_sort: null buffer or workspace too small (%zu < %zu)", ws_bytes,
-                  sd3d_sp_sort_workspace_bytes(N, S));
-        return SD3D_ERR_ARG;
-    }
-    if (N == 0) {
-        cudaMemsetAsync(seg_offsets, 0, (size_t)(S + 2) * sizeof(int32_t), stream);
-        return check_launch("sd3d_sp_sort(memset)");
-    }
+    *done = true;
+    return SD3D_OK;
+}
+
+// sort (+ optional cell keys); the shared body of sd3d_sp_sort and sd3d_sp_plan
+static int run_sort(const int64_t* idx, const float* xyz, float inv_cell, int64_t N, int64_t S, int32_t* perm,
+                    int32_t* seg_offsets, const SortWs& w, cudaStream_t stream) {
+    static bool scan_attr = false;
+    int rc = set_smem_attr_once(reinterpret_cast<const void*>(radix_scan_kernel), kScanCap * (int)sizeof(int32_t),
+                                &scan_attr, "sd3d_sp_sort");
+    if (rc != SD3D_OK) return rc;
     const SortGeom g = sort_geom(N, S);
-    int32_t* hist = reinterpret_cast<int32_t*>(ws);
-    int32_t* bufs = hist + (size_t)(1 << kMaxDigitBits) * kMaxSortBlocks;
-    int32_t* keysA = bufs;
-    int32_t* valsA = bufs + N;
-    int32_t* keysB = bufs + 2 * N;
-    int32_t* valsB = bufs + 3 * N;
+    int32_t* keysA = w.bufs;
+    int32_t* valsA = w.bufs + N;
+    int32_t* keysB = w.bufs + 2 * N;
+    int32_t* valsB = w.bufs + 3 * N;
     const int32_t* kin = nullptr;
     const int32_t* vin = nullptr;
     for (int p = 0; p < g.passes; ++p) {
@@ -441,22 +474,26 @@ extern "C" int sd3d_sp_sort(const int64_t* idx, int64_t N, int64_t S, int32_t* p
         const bool first = (p == 0), last = (p == g.passes - 1);
         int32_t* kout = last ? (g.passes > 1 ? ((p & 1) ? keysB : keysA) : nullptr) : ((p & 1) ? keysB : keysA);
         int32_t* vout = last ? perm : ((p & 1) ? valsB : valsA);
+        uint16_t* cell_out = (last && xyz != nullptr) ? w.cell : nullptr;
         const size_t sm_hist = (size_t)bins * sizeof(int32_t);
         const size_t sm_scat = (size_t)bins * kSortWarps * sizeof(int32_t);
+        const size_t sm_scan = (size_t)bins * g.nb * sizeof(int32_t);
         if (first)
             radix_hist_kernel<true><<<g.nb, kSortThreads, sm_hist, stream>>>(idx, nullptr, N, (int32_t)S, shift, bits,
-                                                                            g.items_per_block, g.nb, hist);
+                                                                            g.items_per_block, g.nb, w.hist);
         else
             radix_hist_kernel<false><<<g.nb, kSortThreads, sm_hist, stream>>>(nullptr, kin, N, (int32_t)S, shift,
-                                                                             bits, g.items_per_block, g.nb, hist);
-        radix_scan_kernel<<<1, 1024, 0, stream>>>(hist, bins, g.nb, (g.passes == 1) ? seg_offsets : nullptr,
-                                                  (int32_t)S, N);
+                                                                             bits, g.items_per_block, g.nb, w.hist);
+        radix_scan_kernel<<<1, 1024, sm_scan, stream>>>(w.hist, bins, g.nb, (g.passes == 1) ? seg_offsets : nullptr,
+                                                        (int32_t)S, N);
         if (first)
             radix_scatter_kernel<true><<<g.nb, kSortThreads, sm_scat, stream>>>(
-                idx, nullptr, nullptr, N, (int32_t)S, shift, bits, g.items_per_block, g.nb, hist, kout, vout);
+                idx, nullptr, nullptr, N, (int32_t)S, shift, bits, g.items_per_block, g.nb, w.hist, kout, vout, xyz,
+                inv_cell, cell_out);
         else
             radix_scatter_kernel<false><<<g.nb, kSortThreads, sm_scat, stream>>>(
-                nullptr, kin, vin, N, (int32_t)S, shift, bits, g.items_per_block, g.nb, hist, kout, vout);
+                nullptr, kin, vin, N, (int32_t)S, shift, bits, g.items_per_block, g.nb, w.hist, kout, vout, xyz,
+                inv_cell, cell_out);
         kin = kout;
         vin = vout;
     }
@@ -464,6 +501,65 @@ extern "C" int sd3d_sp_sort(const int64_t* idx, int64_t N, int64_t S, int32_t* p
         const int64_t threads = N + 1;
         seg_bounds_kernel<<<(unsigned)ceil_div64(threads, 256), 256, 0, stream>>>(kin, N, (int32_t)S, seg_offsets);
     }
+    return SD3D_OK;
+}
+
+static int run_tasks(const int32_t* seg_offsets, const uint32_t* anchor, int64_t S, int run, int32_t* task_offsets,
+                     int32_t* task_seg, int64_t max_tasks, cudaStream_t stream) {
+    // S+1 segments: the superpoints plus the trash segment [seg_offsets[S], seg_offsets[S+1])
+    const int32_t nseg = (int32_t)S + 1;
+    size_t smem = 0;
+    if (anchor != nullptr && nseg <= kMaxOrderedSegs) {
+        int n2 = 1;
+        while (n2 < nseg) n2 <<= 1;
+        smem = (size_t)(nseg <= kMaxRankedSegs ? 2 * kMaxRankedSegs : n2) * sizeof(uint64_t);
+        static bool attr = false;
+        const int rc = set_smem_attr_once(reinterpret_cast<const void*>(sp_tasks_kernel),
+                                          kMaxOrderedSegs * (int)sizeof(uint64_t), &attr, "sd3d_sp_tasks");
+        if (rc != SD3D_OK) return rc;
+    }
+    sp_tasks_kernel<<<1, 1024, smem, stream>>>(seg_offsets, anchor, nseg, run, task_offsets, task_seg, max_tasks);
+    return SD3D_OK;
+}
+
+}  // namespace sd3d
+
+using namespace sd3d;
+
+extern "C" size_t sd3d_sp_sort_workspace_bytes(int64_t N, int64_t S) {
+    if (N < 0) N = 0;
+    if (S < 0) S = 0;
+    return sort_ws_layout(N, S, nullptr, nullptr);
+}
+
+static int check_sort_args(const char* what, const int64_t* idx, int64_t N, int64_t S, const int32_t* perm,
+                           const int32_t* seg_offsets, const void* ws, size_t ws_bytes) {
+    if (N < 0 || S < 0 || N >= (int64_t(1) << 31) - 64 || S >= (int64_t(1) << 30)) {
+        set_error("%s: N=%lld S=%lld out of range", what, (long long)N, (long long)S);
+        return SD3D_ERR_ARG;
+    }
+    if (seg_offsets == nullptr || (N > 0 && (idx == nullptr || perm == nullptr)) || ws == nullptr ||
+        !aligned16(ws) || ws_bytes < sd3d_sp_sort_workspace_bytes(N, S)) {
+        set_error("%s: null buffer or workspace too small (%zu < %zu)", what, ws_bytes,
+                  sd3d_sp_sort_workspace_bytes(N, S));
+        return SD3D_ERR_ARG;
+    }
+    return SD3D_OK;
+}
+
+extern "C" int sd3d_sp_sort(const int64_t* idx, int64_t N, int64_t S, int32_t* perm, int32_t* seg_offsets, void* ws,
+                            size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_sort_args("sd3d_sp_sort", idx, N, S, perm, seg_offsets, ws, ws_bytes);
+    if (rc != SD3D_OK) return rc;
+    if (N == 0) {
+        cudaMemsetAsync(seg_offsets, 0, (size_t)(S + 2) * sizeof(int32_t), stream);
+        return check_launch("sd3d_sp_sort(memset)");
+    }
+    SortWs w;
+    sort_ws_layout(N, S, ws, &w);
+    rc = run_sort(idx, nullptr, 0.f, N, S, perm, seg_offsets, w, stream);
+    if (rc != SD3D_OK) return rc;
     return check_launch("sd3d_sp_sort");
 }
 
@@ -472,44 +568,42 @@ extern "C" int64_t sd3d_sp_max_tasks(int64_t N, int64_t S, int run) {
     return ceil_div64(N, run) + S + 1;
 }
 
-extern "C" int sd3d_sp_refine(const float* xyz, const int32_t* perm, const int32_t* seg_offsets, int64_t N, int64_t S,
-                              int32_t* order, uint32_t* anchor, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
-    if (N < 0 || S < 0 || S >= (int64_t(1) << 30) || seg_offsets == nullptr || anchor == nullptr ||
-        (N > 0 && (xyz == nullptr || perm == nullptr || order == nullptr))) {
-        set_error("sd3d_sp_refine: bad argument");
-        return SD3D_ERR_ARG;
-    }
-    sp_refine_kernel<<<(unsigned)(S + 1), kRefineThreads, 0, stream>>>(xyz, perm, seg_offsets, order, anchor);
-    return check_launch("sd3d_sp_refine");
-}
-
-extern "C" int sd3d_sp_tasks(const int32_t* seg_offsets, const uint32_t* anchor, int64_t S, int run,
-                             int32_t* task_offsets, int32_t* task_seg, int64_t max_tasks, void* stream_) {
+extern "C" int sd3d_sp_tasks(const int32_t* seg_offsets, int64_t S, int run, int32_t* task_offsets, int32_t* task_seg,
+                             int64_t max_tasks, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (seg_offsets == nullptr || task_offsets == nullptr || (task_seg == nullptr && max_tasks > 0) || run <= 0 ||
         S < 0 || S >= (int64_t(1) << 30)) {
         set_error("sd3d_sp_tasks: bad argument");
         return SD3D_ERR_ARG;
     }
-    // S+1 segments: the superpoints plus the trash segment [seg_offsets[S], seg_offsets[S+1])
-    const int32_t nseg = (int32_t)S + 1;
-    size_t smem = 0;
-    if (anchor != nullptr && nseg <= kMaxOrderedSegs) {
-        int n2 = 1;
-        while (n2 < nseg) n2 <<= 1;
-        smem = (size_t)n2 * sizeof(uint64_t);
-        static bool attr_set = false;
-        if (!attr_set) {
-            const cudaError_t e = cudaFuncSetAttribute(sp_tasks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                       kMaxOrderedSegs * (int)sizeof(uint64_t));
-            if (e != cudaSuccess) {
-                set_error("sd3d_sp_tasks: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-                return SD3D_ERR_CUDA;
-            }
-            attr_set = true;
-        }
-    }
-    sp_tasks_kernel<<<1, 1024, smem, stream>>>(seg_offsets, anchor, nseg, run, task_offsets, task_seg, max_tasks);
+    const int rc = run_tasks(seg_offsets, nullptr, S, run, task_offsets, task_seg, max_tasks, stream);
+    if (rc != SD3D_OK) return rc;
     return check_launch("sd3d_sp_tasks");
+}
+
+extern "C" int sd3d_sp_plan(const int64_t* idx, const float* xyz, int64_t N, int64_t S, int run, float cell,
+                            int32_t* perm, int32_t* order, int32_t* seg_offsets, int32_t* task_offsets,
+                            int32_t* task_seg, int64_t max_tasks, void* ws, size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = check_sort_args("sd3d_sp_plan", idx, N, S, perm, seg_offsets, ws, ws_bytes);
+    if (rc != SD3D_OK) return rc;
+    if (task_offsets == nullptr || (task_seg == nullptr && max_tasks > 0) || run <= 0 || !(cell > 0.f) ||
+        max_tasks < sd3d_sp_max_tasks(N, S, run) || (N > 0 && (xyz == nullptr || order == nullptr))) {
+        set_error("sd3d_sp_plan: bad argument (run=%d cell=%g max_tasks=%lld)", run, (double)cell, (long long)max_tasks);
+        return SD3D_ERR_ARG;
+    }
+    SortWs w;
+    sort_ws_layout(N, S, ws, &w);
+    if (N == 0) {
+        cudaMemsetAsync(seg_offsets, 0, (size_t)(S + 2) * sizeof(int32_t), stream);
+        rc = run_tasks(seg_offsets, nullptr, S, run, task_offsets, task_seg, max_tasks, stream);
+        if (rc != SD3D_OK) return rc;
+        return check_launch("sd3d_sp_plan(empty)");
+    }
+    rc = run_sort(idx, xyz, 1.0f / cell, N, S, perm, seg_offsets, w, stream);
+    if (rc != SD3D_OK) return rc;
+    sp_refine_kernel<<<(unsigned)(S + 1), kSortThreads, 0, stream>>>(xyz, perm, w.cell, seg_offsets, order, w.anchor);
+    rc = run_tasks(seg_offsets, w.anchor, S, run, task_offsets, task_seg, max_tasks, stream);
+    if (rc != SD3D_OK) return rc;
+    return check_launch("sd3d_sp_plan");
 }

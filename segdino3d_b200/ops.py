@@ -66,7 +66,7 @@ class SuperpointPlan:
 
 
 def sp_sort(index: torch.Tensor, n_segments: Optional[int] = None, run: int = DEFAULT_RUN,
-            xyz: Optional[torch.Tensor] = None) -> SuperpointPlan:
+            xyz: Optional[torch.Tensor] = None, refine_cell: float = 0.08) -> SuperpointPlan:
     """Stable counting sort of point ids by superpoint id (replaces the implicit grouping of scatter_mean).
 
     With ``xyz`` the plan also carries a spatially refined processing order for the lifting kernels
@@ -92,22 +92,23 @@ def sp_sort(index: torch.Tensor, n_segments: Optional[int] = None, run: int = DE
         seg_offsets = torch.empty(s + 2, dtype=torch.int32, device=dev)
         ws_bytes = int(lib.sd3d_sp_sort_workspace_bytes(n, s))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        check(lib.sd3d_sp_sort(_ptr(index), n, s, _ptr(perm), _ptr(seg_offsets), _ptr(ws), ws_bytes, _stream()),
-              "sd3d_sp_sort")
-        order, anchor = perm, None
+        max_tasks = int(lib.sd3d_sp_max_tasks(n, s, run))
+        task_offsets = torch.empty(s + 2, dtype=torch.int32, device=dev)
+        task_seg = torch.empty(max(max_tasks, 1), dtype=torch.int32, device=dev)
         if xyz is not None:
             _need_cuda("xyz", xyz)
             if xyz.dtype != torch.float32 or tuple(xyz.shape) != (n, 3):
                 raise ValueError("xyz must be float32 [N,3]")
             order = torch.empty(n, dtype=torch.int32, device=dev)
-            anchor = torch.empty(s + 1, dtype=torch.int32, device=dev)
-            check(lib.sd3d_sp_refine(_ptr(xyz.contiguous()), _ptr(perm), _ptr(seg_offsets), n, s, _ptr(order),
-                                     _ptr(anchor), _stream()), "sd3d_sp_refine")
-        max_tasks = int(lib.sd3d_sp_max_tasks(n, s, run))
-        task_offsets = torch.empty(s + 2, dtype=torch.int32, device=dev)
-        task_seg = torch.empty(max(max_tasks, 1), dtype=torch.int32, device=dev)
-        check(lib.sd3d_sp_tasks(_ptr(seg_offsets), _ptr(anchor), s, run, _ptr(task_offsets), _ptr(task_seg), max_tasks,
-                                _stream()), "sd3d_sp_tasks")
+            check(lib.sd3d_sp_plan(_ptr(index), _ptr(xyz.contiguous()), n, s, run, float(refine_cell), _ptr(perm),
+                                   _ptr(order), _ptr(seg_offsets), _ptr(task_offsets), _ptr(task_seg), max_tasks,
+                                   _ptr(ws), ws_bytes, _stream()), "sd3d_sp_plan")
+        else:
+            order = perm
+            check(lib.sd3d_sp_sort(_ptr(index), n, s, _ptr(perm), _ptr(seg_offsets), _ptr(ws), ws_bytes, _stream()),
+                  "sd3d_sp_sort")
+            check(lib.sd3d_sp_tasks(_ptr(seg_offsets), s, run, _ptr(task_offsets), _ptr(task_seg), max_tasks,
+                                    _stream()), "sd3d_sp_tasks")
     return SuperpointPlan(perm, order, seg_offsets, task_offsets, task_seg, n, s, run, max_tasks)
 
 

@@ -65,12 +65,17 @@ def test_sp_refine_permutes_inside_segments_only():
     order = plan.order.cpu().long()
     assert torch.equal(torch.sort(order).values, torch.arange(30_000))
     assert torch.equal(sc.sp_ids[order], sc.sp_ids[perm.long()])       # same superpoint at every sorted position
-    # spatial coherence: consecutive points of the refined order are much closer than in id order
-    big = int((offs[1:] - offs[:-1]).argmax())
-    seg_r = order[offs[big]: offs[big + 1]]
-    seg_p = perm[offs[big]: offs[big + 1]].long()
-    step_r = (sc.xyz[seg_r][1:] - sc.xyz[seg_r][:-1]).norm(dim=1).mean()
-    step_p = (sc.xyz[seg_p][1:] - sc.xyz[seg_p][:-1]).norm(dim=1).mean()
+    # spatial coherence (ordinary superpoints): consecutive points of the refined order are much closer
+    sc2 = make_scene(n_points=30_000, n_views=1, hd=24, wd=32, stride=8, channels=4, seed=18, sp_target=120)
+    plan2 = sd.sp_sort(sc2.sp_ids.to(DEV), sc2.n_superpoints, xyz=sc2.xyz.to(DEV))
+    perm2, offs2 = so.sp_sort_oracle(sc2.sp_ids, sc2.n_superpoints)
+    order2 = plan2.order.cpu().long()
+    assert torch.equal(sc2.sp_ids[order2], sc2.sp_ids[perm2.long()])
+    big = int((offs2[1:] - offs2[:-1]).argmax())
+    seg_r = order2[offs2[big]: offs2[big + 1]]
+    seg_p = perm2[offs2[big]: offs2[big + 1]].long()
+    step_r = (sc2.xyz[seg_r][1:] - sc2.xyz[seg_r][:-1]).norm(dim=1).mean()
+    step_p = (sc2.xyz[seg_p][1:] - sc2.xyz[seg_p][:-1]).norm(dim=1).mean()
     assert float(step_r) < 0.5 * float(step_p)
     t_off, t_seg = plan.task_offsets.cpu().long(), plan.task_seg.cpu().long()
     sizes = torch.cat([offs[1:] - offs[:-1], torch.tensor([30_000 - int(offs[-1])])]).long()
