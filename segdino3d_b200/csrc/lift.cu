@@ -204,13 +204,17 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(const LiftParams 
     const int lane = lane_id();
     const int64_t p0 = ((int64_t)blockIdx.x * kProjWarps + (threadIdx.x >> 5)) * kProjPts;
     if (p0 >= p.N) return;
+    // the warp's points are consecutive in the processing order: spatial neighbours read neighbouring
+    // depth pixels (same 32-byte sectors) instead of one random DRAM sector per (point, view)
+    int64_t pidv[kProjPts];
     float px[kProjPts], py[kProjPts], pz[kProjPts];
 #pragma unroll
     for (int j = 0; j < kProjPts; ++j) {
-        const int64_t pid = min(p0 + j, p.N - 1);
-        px[j] = __ldg(p.xyz + 3 * pid);
-        py[j] = __ldg(p.xyz + 3 * pid + 1);
-        pz[j] = __ldg(p.xyz + 3 * pid + 2);
+        const int64_t pos = min(p0 + j, p.N - 1);
+        pidv[j] = p.order ? (int64_t)p.order[pos] : pos;
+        px[j] = __ldg(p.xyz + 3 * pidv[j]);
+        py[j] = __ldg(p.xyz + 3 * pidv[j] + 1);
+        pz[j] = __ldg(p.xyz + 3 * pidv[j] + 2);
     }
     const int64_t depth_elems = (int64_t)p.Hd * p.Wd;
     const float wd_f = (float)p.Wd, hd_f = (float)p.Hd;
@@ -253,17 +257,17 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(const LiftParams 
         for (int j = 0; j < kProjPts; ++j) {  // phase 2: depth test, pack the predicate
             const bool visible = cand[j] >= 0 && d[j] > 0.f && fabsf(__fsub_rn(d[j], zc[j])) <= p.tau;
             if (vok && p0 + j < p.N) {
-                if (p.pix_idx) p.pix_idx[(int64_t)v * p.N + p0 + j] = visible ? cand[j] : -1;
-                if (p.vis) p.vis[(int64_t)v * p.N + p0 + j] = visible ? 1 : 0;
+                if (p.pix_idx) p.pix_idx[(int64_t)v * p.N + pidv[j]] = visible ? cand[j] : -1;
+                if (p.vis) p.vis[(int64_t)v * p.N + pidv[j]] = visible ? 1 : 0;
             }
             const unsigned m = __ballot_sync(kFull, visible);
-            if (lane == 0 && p0 + j < p.N) masks[(p0 + j) * nchunks + c] = m;
+            if (lane == 0 && p0 + j < p.N) masks[pidv[j] * nchunks + c] = m;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2: bilinear gather + view sum + mean (+ run partial for the fused superpoint pooling), steps a-2/a-3.
+// K2 (default): bilinear gather + view sum + mean (+ run partial for the fused superpoint pooling), steps a-2/a-3.
 // CTA = 4 warps = one run of <= `run` consecutive points of the processing order; warp w takes points
 // w, w+4, ... of the run (neighbouring points at the same time -> shared L1 lines). Per point, lane r
 // re-projects the r-th visible view (cheap ALU, no depth read), then the warp walks the samples in
@@ -398,6 +402,221 @@ __global__ void __launch_bounds__(kLiftThreads) gather_kernel(const LiftParams p
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K2 (alternative, variant bit 1): view-synchronous tile gather.
+// The L2->SM link is the bound of the plain gather (every sample pulls 4 rows = 4*C*sizeof bytes; measured
+// ~10.5 TB/s = the L2 roof), while the points of a spatially compact tile share most of their tap rows
+// when looked at through ONE view (2.8-4x fewer distinct rows per (tile, view), tools/analyze_reuse.py).
+// So a CTA (8 warps) owns a tile of 32 consecutive points of the refined order, every warp keeps the
+// accumulators of its 4 points in registers, and the whole CTA walks the views of the tile IN LOCKSTEP
+// (one __syncthreads per view): all rows of (tile, view) are requested within a short window, the first
+// request of a row goes to L2, the repeats hit L1. Per view, lanes 0..3 re-project their point and build
+// the sample scalars; samples are issued/blended two at a time (register double buffer).
+// Per point the views are still summed in ascending order with the same unfused arithmetic -> the result
+// is bit-identical to gather_kernel and to the oracle.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kTilePts = 32;    // points per tile step
+constexpr int kMaxChunks = 32;  // <= 1024 views per launch
+
+template <int NV, typename FT, bool FAST, bool DB, int kTileG>
+__global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePts / kTileG)))
+    gather_tile_kernel(const LiftParams p, const uint32_t* __restrict__ masks, int nchunks, int flags) {
+    constexpr int kTileWarps = kTilePts / kTileG;
+    const bool do_sync = (flags & 1) == 0, do_prefetch = (flags & 2) == 0;
+    __shared__ uint32_t s_union[kMaxChunks];
+    __shared__ float4 s_red[kTileWarps][NV * 32];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    const int64_t task = blockIdx.x;
+    int64_t start, end;
+    int seg = -1;
+    if (p.pool) {
+        const int32_t n_tasks = p.task_offsets[p.S + 1];
+        if (task >= n_tasks) return;
+        seg = p.task_seg[task];
+        start = (int64_t)p.seg_offsets[seg] + (task - p.task_offsets[seg]) * (int64_t)p.run;
+        end = min(start + (int64_t)p.run, (int64_t)p.seg_offsets[seg + 1]);
+    } else {
+        start = task * (int64_t)p.run;
+        if (start >= p.N) return;
+        end = min(start + (int64_t)p.run, p.N);
+    }
+    const FT* __restrict__ fmap = reinterpret_cast<const FT*>(p.fmap);
+    const int64_t view_elems = (int64_t)p.Hf * p.Wf * p.C;
+    const int row_elems = p.Wf * p.C;
+
+    float4 sp_acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) sp_acc[k] = f4_zero();
+    Sample<NV> sa, sb;
+    sample_clear<NV>(sa);
+    if (DB) sample_clear<NV>(sb);
+
+    for (int64_t t0 = start; t0 < end; t0 += kTilePts) {  // one pass when run == 32
+        // lanes 0..3 of every warp own one point each
+        const int64_t my_pos = t0 + warp * kTileG + lane;
+        const bool own = lane < kTileG && my_pos < end;
+        int32_t my_pid = -1;
+        float mx = 0.f, my = 0.f, mz = 0.f;
+        if (own) {
+            my_pid = p.order ? p.order[my_pos] : (int32_t)my_pos;
+            mx = __ldg(p.xyz + 3 * (int64_t)my_pid);
+            my = __ldg(p.xyz + 3 * (int64_t)my_pid + 1);
+            mz = __ldg(p.xyz + 3 * (int64_t)my_pid + 2);
+        }
+        const uint32_t* __restrict__ mw = masks + (int64_t)max(my_pid, 0) * nchunks;
+        // union of the tile's view masks
+        if (threadIdx.x < kMaxChunks) s_union[threadIdx.x] = 0u;
+        __syncthreads();
+        int my_cnt = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            uint32_t m = own ? __ldg(mw + c) : 0u;
+            my_cnt += __popc(m);
+#pragma unroll
+            for (int o = 1; o < kTileG; o <<= 1) m |= __shfl_xor_sync(kFull, m, o);
+            if (lane == 0 && m) atomicOr(&s_union[c], m);
+        }
+        __syncthreads();
+
+        float4 acc[kTileG][NV];
+#pragma unroll
+        for (int j = 0; j < kTileG; ++j) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) acc[j][k] = f4_zero();
+        }
+        if (p.accumulate) {
+            if (own) my_cnt += p.count[my_pid];
+#pragma unroll
+            for (int j = 0; j < kTileG; ++j) {
+                const int32_t pj = __shfl_sync(kFull, my_pid, j);
+                if (pj >= 0) {
+#pragma unroll
+                    for (int k = 0; k < NV; ++k) {
+                        const int c = (k * 32 + lane) * 4;
+                        if (c < p.C) acc[j][k] = *reinterpret_cast<const float4*>(p.out + (int64_t)pj * p.C + c);
+                    }
+                }
+            }
+        }
+
+        // view iterator over the set bits of s_union (uniform over the CTA), one view of look-ahead:
+        // while view i is blended, the rows of view i+1 are already being prefetched into L1.
+        int it_c = 0;
+        uint32_t it_um = nchunks > 0 ? s_union[0] : 0u;
+        auto next_view = [&](int& chunk) -> int {
+            while (it_um == 0u) {
+                if (++it_c >= nchunks) return -1;
+                it_um = s_union[it_c];
+            }
+            const int b = __ffs(it_um) - 1;
+            it_um &= it_um - 1u;
+            chunk = it_c;
+            return it_c * 32 + b;
+        };
+        auto make_view = [&](int vrel, int chunk, SampleScalars& sc, unsigned& vm) {
+            const bool vis = own && ((__ldg(mw + chunk) >> (vrel & 31)) & 1u);
+            sc.view_flags = 0;
+            sc.o00 = 0;
+            sc.w00 = sc.w01 = sc.w10 = sc.w11 = 0.f;
+            if (vis) {
+                const int v = p.v_begin + vrel;
+                const float4 k4 = ldg_f4(p.K4 + 4 * (int64_t)v);
+                const float4 q0 = ldg_f4(p.w2c + 12 * (int64_t)v);
+                const float4 q1 = ldg_f4(p.w2c + 12 * (int64_t)v + 4);
+                const float4 q2 = ldg_f4(p.w2c + 12 * (int64_t)v + 8);
+                float uu, ww;
+                project_point(k4, q0, q1, q2, mx, my, mz, p.z_near, uu, ww);
+                sc = make_scalars(v, uu, ww, p.stride, p.Hf, p.Wf, p.C);
+            }
+            vm = __ballot_sync(kFull, vis) & ((1u << kTileG) - 1u);
+            // L1 prefetch of the (up to) 4 rows of each visible sample: lane = (row, 128-byte line)
+            const int prow = lane >> 3, pline = lane & 7;
+            const int line_elems = 128 / (int)sizeof(FT);
+            const bool line_ok = do_prefetch && pline * line_elems < p.C;
+#pragma unroll
+            for (int j = 0; j < kTileG; ++j) {
+                if (!do_prefetch) break;
+                if (vm & (1u << j)) {
+                    const int vf = __shfl_sync(kFull, sc.view_flags, j);
+                    const int o00 = __shfl_sync(kFull, sc.o00, j);
+                    if (line_ok && ((vf >> (24 + prow)) & 1)) {
+                        const FT* a = fmap + (int64_t)(vf & 0xFFFFFF) * view_elems + o00 + (prow & 1) * p.C +
+                                      (prow >> 1) * row_elems + pline * line_elems;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+                    }
+                }
+            }
+        };
+
+        SampleScalars cur, nxt;
+        unsigned vm_cur = 0u, vm_nxt = 0u;
+        int chunk_tmp = 0;
+        int v_cur = next_view(chunk_tmp);
+        if (v_cur >= 0) make_view(v_cur, chunk_tmp, cur, vm_cur);
+        while (v_cur >= 0) {
+            const int v_nxt = next_view(chunk_tmp);
+            if (v_nxt >= 0) make_view(v_nxt, chunk_tmp, nxt, vm_nxt);
+            if (DB && kTileG == 4) {
+                // static schedule, two samples in flight: A<-0, B<-1, use A, A<-2, use B, B<-3, use A, use B
+                if (vm_cur & 1u) sample_issue<NV, FT>(sa, cur, 0, fmap, view_elems, p.C, row_elems, lane);
+                if (vm_cur & 2u) sample_issue<NV, FT>(sb, cur, 1, fmap, view_elems, p.C, row_elems, lane);
+                if (vm_cur & 1u) sample_accum<NV, FAST>(acc[0], sa);
+                if (vm_cur & 4u) sample_issue<NV, FT>(sa, cur, 2, fmap, view_elems, p.C, row_elems, lane);
+                if (vm_cur & 2u) sample_accum<NV, FAST>(acc[1], sb);
+                if (vm_cur & 8u) sample_issue<NV, FT>(sb, cur, 3, fmap, view_elems, p.C, row_elems, lane);
+                if (vm_cur & 4u) sample_accum<NV, FAST>(acc[2], sa);
+                if (vm_cur & 8u) sample_accum<NV, FAST>(acc[3], sb);
+            } else {  // rows were prefetched into L1 one view ahead: a single register buffer suffices
+#pragma unroll
+                for (int j = 0; j < kTileG; ++j) {
+                    if (vm_cur & (1u << j)) {
+                        sample_issue<NV, FT>(sa, cur, j, fmap, view_elems, p.C, row_elems, lane);
+                        sample_accum<NV, FAST>(acc[j], sa);
+                    }
+                }
+            }
+            if (do_sync) __syncthreads();  // keep the tile's warps on the same view: their rows meet in L1
+            v_cur = v_nxt;
+            cur = nxt;
+            vm_cur = vm_nxt;
+        }
+
+#pragma unroll
+        for (int j = 0; j < kTileG; ++j) {
+            const int32_t pj = __shfl_sync(kFull, my_pid, j);
+            const int cj = __shfl_sync(kFull, my_cnt, j);
+            if (pj >= 0) {
+                const float denom = (float)max(cj, 1);
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                    const int c = (k * 32 + lane) * 4;
+                    if (c < p.C) {
+                        const float4 o = p.finalize ? f4_div(acc[j][k], denom) : acc[j][k];
+                        st_cs_f4(p.out + (int64_t)pj * p.C + c, o);
+                        sp_acc[k] = f4_add(sp_acc[k], o);
+                    }
+                }
+                if (lane == 0) p.count[pj] = cj;
+            }
+        }
+        __syncthreads();  // s_union is rewritten by the next tile step
+    }
+    if (p.pool && seg < p.S) {  // uniform per CTA
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s_red[warp][k * 32 + lane] = sp_acc[k];
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+                float4 t = s_red[0][k * 32 + lane];
+#pragma unroll
+                for (int w = 1; w < kTileWarps; ++w) t = f4_add(t, s_red[w][k * 32 + lane]);
+                const int c = (k * 32 + lane) * 4;
+                if (c < p.C) *reinterpret_cast<float4*>(p.partials + task * (int64_t)p.C + c) = t;
+            }
+        }
+    }
+}
+
 // out[s,:] = (sum of the run partials of s) / max(n_s,1). Eight lanes share one (superpoint, channel
 // vector): lane j adds partials t0+j, t0+j+8, ... in order, then the eight lane sums are added in lane
 // order -> a fixed summation tree (deterministic), 8x shorter dependent-load chains than a serial walk.
@@ -460,13 +679,26 @@ __global__ void scale_mean_kernel(ScalePtrs ptrs, int L, int64_t numel, float* _
 
 template <int NV, typename FT>
 static void launch_gather(const LiftParams& p, const uint32_t* masks, int nchunks, int64_t n_tasks, bool fast,
-                          cudaStream_t stream) {
+                          bool tile_kernel, bool double_buffer, int tile_flags, cudaStream_t stream) {
     const unsigned grid = (unsigned)n_tasks;
     constexpr bool kPrefetch = NV <= 4;
-    if (fast)
-        gather_kernel<NV, FT, true, kPrefetch><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
-    else
-        gather_kernel<NV, FT, false, kPrefetch><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
+    if (!tile_kernel || NV > 2) {  // point-streaming gather (default; also the only path for wide rows, C > 256)
+        if (fast)
+            gather_kernel<NV, FT, true, kPrefetch><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
+        else
+            gather_kernel<NV, FT, false, kPrefetch><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
+    } else {
+        constexpr int kNV = NV > 2 ? 2 : NV;
+        const int tflags = tile_flags & 3;
+        if (fast && double_buffer)
+            gather_tile_kernel<kNV, FT, true, true, 4><<<grid, 256, 0, stream>>>(p, masks, nchunks, tflags);
+        else if (fast)
+            gather_tile_kernel<kNV, FT, true, false, 4><<<grid, 256, 0, stream>>>(p, masks, nchunks, tflags);
+        else if (double_buffer)
+            gather_tile_kernel<kNV, FT, false, true, 4><<<grid, 256, 0, stream>>>(p, masks, nchunks, tflags);
+        else
+            gather_tile_kernel<kNV, FT, false, false, 4><<<grid, 256, 0, stream>>>(p, masks, nchunks, tflags);
+    }
 }
 
 template <typename FT>
@@ -474,10 +706,13 @@ static int dispatch_gather(const LiftParams& p, const uint32_t* masks, int nchun
                            cudaStream_t stream) {
     const int nv = (p.C + 127) / 128;
     const bool fast = (variant & 1) != 0;
-    if (nv == 1) launch_gather<1, FT>(p, masks, nchunks, n_tasks, fast, stream);
-    else if (nv == 2) launch_gather<2, FT>(p, masks, nchunks, n_tasks, fast, stream);
-    else if (nv <= 4) launch_gather<4, FT>(p, masks, nchunks, n_tasks, fast, stream);
-    else if (nv <= 8) launch_gather<8, FT>(p, masks, nchunks, n_tasks, fast, stream);
+    const bool tk = (variant & 2) != 0 && nchunks <= kMaxChunks;
+    const bool db = (variant & 4) != 0;
+    const int tf = (variant >> 3) & 3;  // tile-kernel experiment bits: 8 = no per-view barrier, 16 = no L1 prefetch
+    if (nv == 1) launch_gather<1, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);
+    else if (nv == 2) launch_gather<2, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);
+    else if (nv <= 4) launch_gather<4, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);
+    else if (nv <= 8) launch_gather<8, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);
     else {
         set_error("sd3d_lift: C=%d > 1024 unsupported", p.C);
         return SD3D_ERR_UNSUPPORTED;

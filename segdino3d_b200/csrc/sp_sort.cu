@@ -42,6 +42,10 @@ static SortGeom sort_geom(int64_t N, int64_t S) {
     const int max_bins = 1 << (g.passes == 1 ? kb : g.bits_per_pass);
     int nb_cap = kScanCap / max_bins;
     if (nb_cap > kMaxSortBlocks) nb_cap = kMaxSortBlocks;
+    // the passes are latency-bound at ScanNet sizes: few, fat blocks keep the [bins][blocks] matrix (and the
+    // single-CTA scan over it) small; >= 4096 items per block
+    const int64_t by_size = N / 4096 > 8 ? N / 4096 : 8;
+    if (nb_cap > by_size) nb_cap = (int)by_size;
     int64_t t = ceil_div64(N > 0 ? N : 1, nb_cap);
     t = ceil_div64(t, kSortThreads) * kSortThreads;
     if (t < 1024) t = 1024;

@@ -66,7 +66,7 @@ def test_sp_refine_permutes_inside_segments_only():
     assert torch.equal(torch.sort(order).values, torch.arange(30_000))
     assert torch.equal(sc.sp_ids[order], sc.sp_ids[perm.long()])       # same superpoint at every sorted position
     # spatial coherence (ordinary superpoints): consecutive points of the refined order are much closer
-    sc2 = make_scene(n_points=30_000, n_views=1, hd=24, wd=32, stride=8, channels=4, seed=18, sp_target=120)
+    sc2 = make_scene(n_points=30_000, n_views=1, hd=24, wd=32, stride=8, channels=4, seed=18, sp_target=None)
     plan2 = sd.sp_sort(sc2.sp_ids.to(DEV), sc2.n_superpoints, xyz=sc2.xyz.to(DEV))
     perm2, offs2 = so.sp_sort_oracle(sc2.sp_ids, sc2.n_superpoints)
     order2 = plan2.order.cpu().long()
@@ -212,6 +212,21 @@ def test_lift_golden_fixture(golden):
 def test_lift_channel_widths(channels):
     sc = make_scene(n_points=3000, n_views=7, hd=60, wd=80, stride=4, channels=channels, seed=channels, sp_target=30)
     _check_lift(sc)
+
+
+@pytest.mark.parametrize("variant", [0, 2, 6, 26])
+@pytest.mark.parametrize("run", [32, 80])
+def test_lift_kernel_variants_bit_exact(variant, run):
+    """point-streaming kernel (default) and the tile kernel (bit 1, with its tuning bits), with and without a
+    plan, any run length."""
+    sc = make_scene(n_points=6000, n_views=40, hd=120, wd=160, stride=8, channels=256, seed=23, sp_target=50)
+    a, c, p, v = _check_lift(sc, variant=variant)
+    d = sc.to(DEV)
+    plan = sd.sp_sort(d.sp_ids, sc.n_superpoints, run=run, xyz=d.xyz)
+    r = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan, pool=True, variant=variant)
+    assert torch.equal(r["feat"].cpu(), lo.lift_finalize_oracle(a, c)) and torch.equal(r["count"].cpu(), c)
+    sp_o = so.scatter_mean_oracle(lo.lift_finalize_oracle(a, c), sc.sp_ids, dim=0)
+    assert rel_row_err(r["sp_feat"], sp_o, floor=0.1) <= 1e-5
 
 
 def test_lift_fma_variant_within_tolerance():
