@@ -48,7 +48,7 @@ class ScenePipeline:
         if torch.device(device).type != "cuda":
             raise ops.Sd3dError("ScenePipeline needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
-        self.depth, self.run, self.variant, self.tau, self.z_near, self.refine = depth, run, variant, tau, z_near, refine
+        self.depth, self.run_len, self.variant, self.tau, self.z_near, self.refine = depth, run, variant, tau, z_near, refine
         with torch.cuda.device(self.device):
             self.s_in = torch.cuda.Stream()
             self.s_comp = torch.cuda.Stream()
@@ -80,7 +80,7 @@ class ScenePipeline:
         with torch.cuda.stream(self.s_comp):
             self.s_comp.wait_event(slot.ev_h2d)
             self.s_comp.wait_event(slot.ev_d2h)  # the previous outputs of this slot have left the device
-            plan = ops.sp_sort(d["sp_ids"], n_sp, run=self.run, xyz=d["xyz"] if self.refine else None)
+            plan = ops.sp_sort(d["sp_ids"], n_sp, run=self.run_len, xyz=d["xyz"] if self.refine else None)
             r = ops.lift(d["xyz"], d["K"], d["w2c"], d["depth"], d["fmap"], stride, tau=self.tau, z_near=self.z_near,
                          plan=plan, pool=True, variant=self.variant)
             slot.out_dev = (r["feat"], r["count"], r["sp_feat"], plan)
