@@ -108,7 +108,9 @@ int sd3d_sp_mean(const float* src, const int32_t* perm, const int32_t* seg_offse
  *   bit-masks written by the projection kernel (+ the run partials when pool != 0, at offset 0).
  * variant: bit 0 = contract the bilinear blend into FFMA (not bit-exact to Appendix A, <= 1e-6 rel.);
  *   bit 1 = view-synchronous tile gather kernel instead of the point-streaming one (same results; bits 2-4
- *   tune it: 4 = register double buffer, 8 = no per-view barrier, 16 = no L1 prefetch).
+ *   tune it: 4 = register double buffer, 8 = no per-view barrier, 16 = no L1 prefetch);
+ *   bit 8 (256) = run the projection kernel only, bit 9 (512) = run the gather kernel only on the masks a
+ *   previous projection-only call left in the same ws (per-kernel timing, stream overlap).
  * --------------------------------------------------------------------------------------------- */
 size_t sd3d_lift_workspace_bytes(int64_t N, int n_views, int C, int64_t max_tasks);
 int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin, int view_end,

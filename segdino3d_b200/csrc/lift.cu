@@ -796,8 +796,10 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
     p.task_offsets = task_offsets; p.task_seg = task_seg; p.S = (int32_t)S; p.run = run;
     p.partials = reinterpret_cast<float*>(ws);
     const int64_t n_tasks = pool ? max_tasks : ceil_div64(N, run);
-    if (nchunks > 0)
+    const bool do_project = (variant & 512) == 0, do_gather = (variant & 256) == 0;
+    if (do_project && nchunks > 0)
         project_kernel<<<(unsigned)ceil_div64(N, kProjWarps * kProjPts), kProjThreads, 0, stream>>>(p, masks, nchunks);
+    if (!do_gather) return check_launch("sd3d_lift(project)");
     int rc;
     switch (fmap_dtype) {
         case SD3D_F32: rc = dispatch_gather<float>(p, masks, nchunks, n_tasks, variant, stream); break;

@@ -267,18 +267,23 @@ def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Ten
             sp_out = torch.empty(s, c, dtype=torch.float32, device=dev)
         ws_bytes = int(lib.sd3d_lift_workspace_bytes(n, ve - vb, c, plan.max_tasks if pool else 0))
         ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-        if events is not None:
+        def call(stage_bits):
+            check(lib.sd3d_lift(_ptr(xyz), n, _ptr(K), _ptr(w2c), v, vb, ve, _ptr(depth), _DEPTH_CODE[depth.dtype], hd, wd,
+                                _ptr(fmap), _FMAP_CODE[fmap.dtype], hf, wf, c, float(stride), float(tau), float(z_near),
+                                1 if accumulate_into is not None else 0, 1 if finalize else 0,
+                                _ptr(plan.order) if plan is not None else None, _ptr(feat), _ptr(count), _ptr(pix),
+                                _ptr(vis), _ptr(plan.seg_offsets) if plan is not None else None, s,
+                                _ptr(plan.task_offsets) if plan is not None else None,
+                                _ptr(plan.task_seg) if plan is not None else None,
+                                plan.max_tasks if plan is not None else 0, plan.run if plan is not None else DEFAULT_RUN,
+                                _ptr(ws), ws_bytes, 1 if pool else 0, int(variant) | stage_bits, _stream()), "sd3d_lift")
+
+        if events is None:
+            call(0)
+        else:  # bench only: bracket the gather kernel alone
+            call(256)
             events[0].record()
-        check(lib.sd3d_lift(_ptr(xyz), n, _ptr(K), _ptr(w2c), v, vb, ve, _ptr(depth), _DEPTH_CODE[depth.dtype], hd, wd,
-                            _ptr(fmap), _FMAP_CODE[fmap.dtype], hf, wf, c, float(stride), float(tau), float(z_near),
-                            1 if accumulate_into is not None else 0, 1 if finalize else 0,
-                            _ptr(plan.order) if plan is not None else None, _ptr(feat), _ptr(count), _ptr(pix),
-                            _ptr(vis), _ptr(plan.seg_offsets) if plan is not None else None, s,
-                            _ptr(plan.task_offsets) if plan is not None else None,
-                            _ptr(plan.task_seg) if plan is not None else None,
-                            plan.max_tasks if plan is not None else 0, plan.run if plan is not None else DEFAULT_RUN,
-                            _ptr(ws), ws_bytes, 1 if pool else 0, int(variant), _stream()), "sd3d_lift")
-        if events is not None:
+            call(512)
             events[1].record()
         if pool:
             check(lib.sd3d_sp_combine(_ptr(ws), _ptr(plan.task_offsets), _ptr(plan.seg_offsets), s, c, plan.run,
