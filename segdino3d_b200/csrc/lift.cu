@@ -274,8 +274,8 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(const LiftParams 
 // ascending view order with LANE = CHANNEL VECTOR and a two-deep register prefetch (sample i+1's tap
 // rows are in flight while sample i is blended).
 // ---------------------------------------------------------------------------------------------------
-template <int NV, typename FT, bool FAST, bool PREFETCH>
-__global__ void __launch_bounds__(kLiftThreads) gather_kernel(const LiftParams p, const uint32_t* __restrict__ masks,
+template <int NV, typename FT, bool FAST, bool PREFETCH, int MINB>
+__global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftParams p, const uint32_t* __restrict__ masks,
                                                               int nchunks) {
     __shared__ float4 s_red[kLiftWarps][NV * 32];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -683,10 +683,19 @@ static void launch_gather(const LiftParams& p, const uint32_t* masks, int nchunk
     const unsigned grid = (unsigned)n_tasks;
     constexpr bool kPrefetch = NV <= 4;
     if (!tile_kernel || NV > 2) {  // point-streaming gather (default; also the only path for wide rows, C > 256)
-        if (fast)
-            gather_kernel<NV, FT, true, kPrefetch><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
-        else
-            gather_kernel<NV, FT, false, kPrefetch><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
+        // registers: 4 CTAs/SM (<=128 regs) is the default; the occupancy variants are for C<=256 only
+        constexpr bool kVar = NV <= 2;
+        const int occ = kVar ? (tile_flags >> 2) & 3 : 0;  // 0: 4 CTAs/SM, 1: 5 CTAs/SM (spills), 2: 3 CTAs/SM
+        if (occ == 1) {
+            if (fast) gather_kernel<NV, FT, true, kPrefetch, (kVar ? 5 : 1)><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
+            else gather_kernel<NV, FT, false, kPrefetch, (kVar ? 5 : 1)><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
+        } else if (occ == 2) {
+            if (fast) gather_kernel<NV, FT, true, kPrefetch, (kVar ? 3 : 1)><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
+            else gather_kernel<NV, FT, false, kPrefetch, (kVar ? 3 : 1)><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
+        } else {
+            if (fast) gather_kernel<NV, FT, true, kPrefetch, (kVar ? 4 : 1)><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
+            else gather_kernel<NV, FT, false, kPrefetch, (kVar ? 4 : 1)><<<grid, kLiftThreads, 0, stream>>>(p, masks, nchunks);
+        }
     } else {
         constexpr int kNV = NV > 2 ? 2 : NV;
         const int tflags = tile_flags & 3;
@@ -708,7 +717,8 @@ static int dispatch_gather(const LiftParams& p, const uint32_t* masks, int nchun
     const bool fast = (variant & 1) != 0;
     const bool tk = (variant & 2) != 0 && nchunks <= kMaxChunks;
     const bool db = (variant & 4) != 0;
-    const int tf = (variant >> 3) & 3;  // tile-kernel experiment bits: 8 = no per-view barrier, 16 = no L1 prefetch
+    const int tf = (variant >> 3) & 15;  // experiment bits: 8 = tile: no per-view barrier, 16 = tile: no L1 prefetch,
+                                         // 32 / 64 = streaming kernel compiled for 5 / 3 CTAs per SM
     if (nv == 1) launch_gather<1, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);
     else if (nv == 2) launch_gather<2, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);
     else if (nv <= 4) launch_gather<4, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);
@@ -768,9 +778,10 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
     }
     const bool pool = pool_ != 0;
     if (run <= 0) run = 32;
+    const bool do_project = (variant & 512) == 0, do_gather = (variant & 256) == 0;
     if (pool) {
-        if (!finalize || order == nullptr || seg_offsets == nullptr || task_offsets == nullptr ||
-            task_seg == nullptr || S < 0 || max_tasks < sd3d_sp_max_tasks(N, S, run)) {
+        if (!finalize || S < 0 || max_tasks < sd3d_sp_max_tasks(N, S, run) ||
+            (do_gather && (order == nullptr || seg_offsets == nullptr || task_offsets == nullptr || task_seg == nullptr))) {
             set_error("sd3d_lift: fused pooling needs finalize=1, order, seg_offsets and the task tables");
             return SD3D_ERR_ARG;
         }
@@ -796,7 +807,6 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
     p.task_offsets = task_offsets; p.task_seg = task_seg; p.S = (int32_t)S; p.run = run;
     p.partials = reinterpret_cast<float*>(ws);
     const int64_t n_tasks = pool ? max_tasks : ceil_div64(N, run);
-    const bool do_project = (variant & 512) == 0, do_gather = (variant & 256) == 0;
     if (do_project && nchunks > 0)
         project_kernel<<<(unsigned)ceil_div64(N, kProjWarps * kProjPts), kProjThreads, 0, stream>>>(p, masks, nchunks);
     if (!do_gather) return check_launch("sd3d_lift(project)");

@@ -18,7 +18,11 @@
 //   refine = per-superpoint stable counting sort by the cell key (one CTA per superpoint, 512 bins)
 //   tasks  = superpoints ranked along the world Morton curve, ceil(n_s/run) runs each (ONE CTA).
 // Keys outside [0,S) are mapped to the extra key S ("trash"), which sorts last.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace sd3d {
 
@@ -42,10 +46,12 @@ static SortGeom sort_geom(int64_t N, int64_t S) {
     const int max_bins = 1 << (g.passes == 1 ? kb : g.bits_per_pass);
     int nb_cap = kScanCap / max_bins;
     if (nb_cap > kMaxSortBlocks) nb_cap = kMaxSortBlocks;
-    // the passes are latency-bound at ScanNet sizes: few, fat blocks keep the [bins][blocks] matrix (and the
-    // single-CTA scan over it) small; >= 4096 items per block
-    const int64_t by_size = N / 4096 > 8 ? N / 4096 : 8;
+    // the passes are latency-bound at ScanNet sizes: ~2048 items per block keeps the per-warp serial chain of
+    // the stable scatter short (8 steps) while the [bins][blocks] matrix still fits one CTA's shared memory;
+    // <= kFusedMaxBlocks blocks so that the pass can run as one cooperative kernel
+    const int64_t by_size = N / 2048 > 8 ? N / 2048 : 8;
     if (nb_cap > by_size) nb_cap = (int)by_size;
+    if (nb_cap > 128) nb_cap = 128;
     int64_t t = ceil_div64(N > 0 ? N : 1, nb_cap);
     t = ceil_div64(t, kSortThreads) * kSortThreads;
     if (t < 1024) t = 1024;
@@ -222,6 +228,145 @@ __global__ void __launch_bounds__(kSortThreads)
     }
 }
 
+// One radix pass as ONE cooperative kernel: hist -> grid.sync -> scan (block 0) -> grid.sync -> scatter.
+// At ScanNet sizes every phase is a few microseconds of latency, so the two kernel boundaries (launch gap +
+// tail + ramp) cost more than the work; the grid barrier replaces them. Same arithmetic as the three
+// separate kernels (which remain the fallback when the grid cannot be co-resident).
+constexpr int kFusedMaxBlocks = 128;
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kSortThreads)
+    radix_pass_fused_kernel(const int64_t* __restrict__ idx, const int32_t* __restrict__ keys_in,
+                            const int32_t* __restrict__ vals_in, int64_t N, int32_t S, int shift, int bits,
+                            int items_per_block, int nb, int32_t* __restrict__ hist, int32_t* __restrict__ keys_out,
+                            int32_t* __restrict__ vals_out, const float* __restrict__ xyz, float inv_cell,
+                            uint16_t* __restrict__ cell_out, int32_t* __restrict__ seg_offsets) {
+    extern __shared__ int32_t s_dyn[];
+    __shared__ int32_t s_rowbase[1 << kMaxDigitBits];
+    __shared__ int32_t s_warp[kSortWarps];
+    cg::grid_group grid = cg::this_grid();
+    const int bins = 1 << bits;
+    const int lane = lane_id(), warp = threadIdx.x >> 5, tid = threadIdx.x;
+    const int64_t beg = (int64_t)blockIdx.x * items_per_block;
+    const int64_t end = min(beg + (int64_t)items_per_block, N);
+    // ---- phase 1: per-block digit histogram
+    for (int i = tid; i < bins; i += kSortThreads) s_dyn[i] = 0;
+    __syncthreads();
+    for (int64_t i = beg + tid; i < end; i += kSortThreads) {
+        const int32_t key = FIRST ? clamp_key(idx[i], S) : keys_in[i];
+        atomicAdd(&s_dyn[(key >> shift) & (bins - 1)], 1);
+    }
+    __syncthreads();
+    for (int i = tid; i < bins; i += kSortThreads) hist[(int64_t)i * nb + blockIdx.x] = s_dyn[i];
+    grid.sync();
+    // ---- phase 2: block 0 scans the [bins][nb] matrix (staged in its shared memory)
+    if (blockIdx.x == 0) {
+        const int total = bins * nb;
+        for (int i = tid; i < total; i += kSortThreads) s_dyn[i] = hist[i];
+        __syncthreads();
+        for (int row = warp; row < bins; row += kSortWarps) {
+            int32_t* r = s_dyn + row * nb;
+            int32_t carry = 0;
+            for (int c0 = 0; c0 < nb; c0 += 32) {
+                const int col = c0 + lane;
+                const int32_t v = col < nb ? r[col] : 0;
+                int32_t inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int32_t n = __shfl_up_sync(kFull, inc, o);
+                    if (lane >= o) inc += n;
+                }
+                if (col < nb) r[col] = carry + inc - v;
+                carry += __shfl_sync(kFull, inc, 31);
+            }
+            if (lane == 0) s_rowbase[row] = carry;
+        }
+        __syncthreads();
+        {  // exclusive scan of the row totals: 4 consecutive bins per thread (bins <= 1024)
+            int32_t t[4], tsum = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int b = tid * 4 + k;
+                t[k] = b < bins ? s_rowbase[b] : 0;
+                tsum += t[k];
+            }
+            int32_t inc = tsum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int32_t n = __shfl_up_sync(kFull, inc, o);
+                if (lane >= o) inc += n;
+            }
+            if (lane == 31) s_warp[warp] = inc;
+            __syncthreads();
+            int32_t wbase = 0;
+            for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+            int32_t excl = wbase + inc - tsum;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int b = tid * 4 + k;
+                if (b < bins) s_rowbase[b] = excl;
+                excl += t[k];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < total; i += kSortThreads) hist[i] = s_dyn[i] + s_rowbase[i / nb];
+        if (seg_offsets != nullptr) {
+            for (int s = tid; s <= S; s += kSortThreads) seg_offsets[s] = s_rowbase[s];
+            if (tid == 0) seg_offsets[S + 1] = (int32_t)N;
+        }
+    }
+    grid.sync();
+    // ---- phase 3: stable scatter (identical to radix_scatter_kernel)
+    int32_t* s_cnt = s_dyn;  // [kSortWarps][bins]
+    for (int i = tid; i < bins * kSortWarps; i += kSortThreads) s_cnt[i] = 0;
+    __syncthreads();
+    const int per_warp = items_per_block / kSortWarps;
+    const int64_t wbeg = min(beg + (int64_t)warp * per_warp, end);
+    const int64_t wend = min(wbeg + (int64_t)per_warp, end);
+    int32_t* my_cnt = s_cnt + warp * bins;
+    for (int64_t i = wbeg + lane; i < wend; i += 32) {
+        const int32_t key = FIRST ? clamp_key(idx[i], S) : keys_in[i];
+        atomicAdd(&my_cnt[(key >> shift) & (bins - 1)], 1);
+    }
+    __syncthreads();
+    for (int b = tid; b < bins; b += kSortThreads) {
+        int32_t run = hist[(int64_t)b * nb + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const int32_t c = s_cnt[w * bins + b];
+            s_cnt[w * bins + b] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    for (int64_t i0 = wbeg; i0 < wend; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const bool active = i < wend;
+        int32_t key = 0, digit = bins;
+        if (active) {
+            key = FIRST ? clamp_key(idx[i], S) : keys_in[i];
+            digit = (key >> shift) & (bins - 1);
+        }
+        const unsigned peers = __match_any_sync(kFull, digit);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        int32_t dst = 0;
+        if (active) dst = my_cnt[digit] + rank;
+        __syncwarp();
+        if (active && rank == 0) my_cnt[digit] += __popc(peers);
+        __syncwarp();
+        if (active) {
+            const int32_t val = FIRST ? (int32_t)i : vals_in[i];
+            if (keys_out != nullptr) keys_out[dst] = key;
+            vals_out[dst] = val;
+            if (cell_out != nullptr) {
+                const float x = __ldg(xyz + 3 * (int64_t)val), y = __ldg(xyz + 3 * (int64_t)val + 1),
+                            z = __ldg(xyz + 3 * (int64_t)val + 2);
+                cell_out[dst] = (uint16_t)cell_key9(x, y, z, inv_cell);
+            }
+        }
+    }
+}
+
 // seg_offsets[s] = first sorted position whose key >= s, for s in [0,S]  (multi-pass case)
 __global__ void seg_bounds_kernel(const int32_t* __restrict__ sorted_keys, int64_t N, int32_t S,
                                   int32_t* __restrict__ seg_offsets) {
@@ -243,24 +388,15 @@ constexpr int kRefineBins = 512;
 __global__ void __launch_bounds__(kSortThreads)
     sp_refine_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ perm,
                      const uint16_t* __restrict__ cell, const int32_t* __restrict__ seg_offsets,
-                     int32_t* __restrict__ order, uint32_t* __restrict__ anchor) {
+                     int32_t* __restrict__ order) {
     __shared__ int32_t s_cnt[kSortWarps][kRefineBins];
     __shared__ int32_t s_tot[kRefineBins];
     __shared__ int32_t s_warp[kSortWarps];
     const int seg = blockIdx.x;
     const int beg = seg_offsets[seg], end = seg_offsets[seg + 1];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    if (end <= beg) {
-        if (threadIdx.x == 0) anchor[seg] = 0x7FFFFFFFu;
-        return;
-    }
-    if (threadIdx.x == 0) {
-        const int32_t p0 = perm[beg];
-        const int gx = min(max((int)floorf(__ldg(xyz + 3 * (int64_t)p0) * 4.0f) + 512, 0), 1023);
-        const int gy = min(max((int)floorf(__ldg(xyz + 3 * (int64_t)p0 + 1) * 4.0f) + 512, 0), 1023);
-        const int gz = min(max((int)floorf(__ldg(xyz + 3 * (int64_t)p0 + 2) * 4.0f) + 512, 0), 1023);
-        anchor[seg] = morton30(gx, gy, gz);
-    }
+    if (end <= beg) return;
+    (void)xyz;
     for (int i = threadIdx.x; i < kSortWarps * kRefineBins; i += blockDim.x) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     const int n = end - beg;
@@ -345,20 +481,34 @@ __device__ __forceinline__ void bitonic_sort_smem(uint64_t* items, int n2) {
 constexpr int kMaxOrderedSegs = 8192;
 constexpr int kMaxRankedSegs = 1024;
 
+__device__ __forceinline__ uint32_t seg_anchor(const int32_t* __restrict__ seg_offsets, const int32_t* __restrict__ perm,
+                                               const float* __restrict__ xyz, int seg) {
+    // world-grid Morton key (0.25 m cells, origin -128 m) of the first point of the segment
+    const int beg = seg_offsets[seg], end = seg_offsets[seg + 1];
+    if (end <= beg) return 0x7FFFFFFFu;
+    const int32_t p0 = perm[beg];
+    const int gx = min(max((int)floorf(__ldg(xyz + 3 * (int64_t)p0) * 4.0f) + 512, 0), 1023);
+    const int gy = min(max((int)floorf(__ldg(xyz + 3 * (int64_t)p0 + 1) * 4.0f) + 512, 0), 1023);
+    const int gz = min(max((int)floorf(__ldg(xyz + 3 * (int64_t)p0 + 2) * 4.0f) + 512, 0), 1023);
+    return morton30(gx, gy, gz);
+}
+
 __global__ void __launch_bounds__(1024) sp_tasks_kernel(const int32_t* __restrict__ seg_offsets,
-                                                        const uint32_t* __restrict__ anchor, int32_t nseg, int run,
+                                                        const int32_t* __restrict__ perm,
+                                                        const float* __restrict__ xyz, int32_t nseg, int run,
                                                         int32_t* __restrict__ task_offsets,
                                                         int32_t* __restrict__ task_seg, int64_t max_tasks) {
     extern __shared__ uint64_t s_sorted[];  // [n2] (anchor << 32 | seg) when ordering is on
     __shared__ int32_t s_warp[32];
     __shared__ int32_t s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool ordered = anchor != nullptr && nseg <= kMaxOrderedSegs;
+    const bool ordered = xyz != nullptr && nseg <= kMaxOrderedSegs;
     if (ordered) {
         // the trash segment (last) gets the largest key so that it stays at the end
         if (nseg <= kMaxRankedSegs) {
             uint64_t mine = ~uint64_t(0);
-            if (tid < nseg) mine = ((uint64_t)(tid == nseg - 1 ? 0xFFFFFFFEu : anchor[tid]) << 32) | (uint32_t)tid;
+            if (tid < nseg)
+                mine = ((uint64_t)(tid == nseg - 1 ? 0xFFFFFFFEu : seg_anchor(seg_offsets, perm, xyz, tid)) << 32) | (uint32_t)tid;
             s_sorted[kMaxRankedSegs + tid] = mine;  // staging half
             __syncthreads();
             if (tid < nseg) {
@@ -372,7 +522,8 @@ __global__ void __launch_bounds__(1024) sp_tasks_kernel(const int32_t* __restric
             while (n2 < nseg) n2 <<= 1;
             for (int i = tid; i < n2; i += blockDim.x) {
                 uint64_t item = ~uint64_t(0);
-                if (i < nseg) item = ((uint64_t)(i == nseg - 1 ? 0xFFFFFFFEu : anchor[i]) << 32) | (uint32_t)i;
+                if (i < nseg)
+                    item = ((uint64_t)(i == nseg - 1 ? 0xFFFFFFFEu : seg_anchor(seg_offsets, perm, xyz, i)) << 32) | (uint32_t)i;
                 s_sorted[i] = item;
             }
             __syncthreads();
@@ -482,22 +633,46 @@ static int run_sort(const int64_t* idx, const float* xyz, float inv_cell, int64_
         const size_t sm_hist = (size_t)bins * sizeof(int32_t);
         const size_t sm_scat = (size_t)bins * kSortWarps * sizeof(int32_t);
         const size_t sm_scan = (size_t)bins * g.nb * sizeof(int32_t);
-        if (first)
-            radix_hist_kernel<true><<<g.nb, kSortThreads, sm_hist, stream>>>(idx, nullptr, N, (int32_t)S, shift, bits,
-                                                                            g.items_per_block, g.nb, w.hist);
-        else
-            radix_hist_kernel<false><<<g.nb, kSortThreads, sm_hist, stream>>>(nullptr, kin, N, (int32_t)S, shift,
-                                                                             bits, g.items_per_block, g.nb, w.hist);
-        radix_scan_kernel<<<1, 1024, sm_scan, stream>>>(w.hist, bins, g.nb, (g.passes == 1) ? seg_offsets : nullptr,
-                                                        (int32_t)S, N);
-        if (first)
-            radix_scatter_kernel<true><<<g.nb, kSortThreads, sm_scat, stream>>>(
-                idx, nullptr, nullptr, N, (int32_t)S, shift, bits, g.items_per_block, g.nb, w.hist, kout, vout, xyz,
-                inv_cell, cell_out);
-        else
-            radix_scatter_kernel<false><<<g.nb, kSortThreads, sm_scat, stream>>>(
-                nullptr, kin, vin, N, (int32_t)S, shift, bits, g.items_per_block, g.nb, w.hist, kout, vout, xyz,
-                inv_cell, cell_out);
+        const size_t sm_fused = sm_scan > sm_scat ? sm_scan : sm_scat;
+        bool fused_done = false;
+        if (g.nb <= kFusedMaxBlocks) {
+            int32_t S32 = (int32_t)S;
+            int shift_ = shift, bits_ = bits, ipb = g.items_per_block, nb_ = g.nb;
+            int32_t* hist_ = w.hist;
+            int32_t* seg_ = (g.passes == 1) ? seg_offsets : nullptr;
+            const int64_t* idx_ = first ? idx : nullptr;
+            const int32_t* kin_ = first ? nullptr : kin;
+            const int32_t* vin_ = first ? nullptr : vin;
+            void* args[] = {(void*)&idx_, (void*)&kin_, (void*)&vin_, (void*)&N, (void*)&S32, (void*)&shift_,
+                            (void*)&bits_, (void*)&ipb, (void*)&nb_, (void*)&hist_, (void*)&kout, (void*)&vout,
+                            (void*)&xyz, (void*)&inv_cell, (void*)&cell_out, (void*)&seg_};
+            const void* fn = first ? reinterpret_cast<const void*>(radix_pass_fused_kernel<true>)
+                                   : reinterpret_cast<const void*>(radix_pass_fused_kernel<false>);
+            static bool attr_t = false, attr_f = false;
+            rc = set_smem_attr_once(fn, kScanCap * (int)sizeof(int32_t), first ? &attr_t : &attr_f, "sd3d_sp_sort");
+            if (rc != SD3D_OK) return rc;
+            const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(g.nb), dim3(kSortThreads), args, sm_fused, stream);
+            if (e == cudaSuccess) fused_done = true;
+            else cudaGetLastError();  // not co-resident / unsupported: fall back to the three-kernel pass
+        }
+        if (!fused_done) {
+            if (first)
+                radix_hist_kernel<true><<<g.nb, kSortThreads, sm_hist, stream>>>(idx, nullptr, N, (int32_t)S, shift, bits,
+                                                                                g.items_per_block, g.nb, w.hist);
+            else
+                radix_hist_kernel<false><<<g.nb, kSortThreads, sm_hist, stream>>>(nullptr, kin, N, (int32_t)S, shift,
+                                                                                 bits, g.items_per_block, g.nb, w.hist);
+            radix_scan_kernel<<<1, 1024, sm_scan, stream>>>(w.hist, bins, g.nb, (g.passes == 1) ? seg_offsets : nullptr,
+                                                            (int32_t)S, N);
+            if (first)
+                radix_scatter_kernel<true><<<g.nb, kSortThreads, sm_scat, stream>>>(
+                    idx, nullptr, nullptr, N, (int32_t)S, shift, bits, g.items_per_block, g.nb, w.hist, kout, vout, xyz,
+                    inv_cell, cell_out);
+            else
+                radix_scatter_kernel<false><<<g.nb, kSortThreads, sm_scat, stream>>>(
+                    nullptr, kin, vin, N, (int32_t)S, shift, bits, g.items_per_block, g.nb, w.hist, kout, vout, xyz,
+                    inv_cell, cell_out);
+        }
         kin = kout;
         vin = vout;
     }
@@ -508,12 +683,12 @@ static int run_sort(const int64_t* idx, const float* xyz, float inv_cell, int64_
     return SD3D_OK;
 }
 
-static int run_tasks(const int32_t* seg_offsets, const uint32_t* anchor, int64_t S, int run, int32_t* task_offsets,
-                     int32_t* task_seg, int64_t max_tasks, cudaStream_t stream) {
+static int run_tasks(const int32_t* seg_offsets, const int32_t* perm, const float* xyz, int64_t S, int run,
+                     int32_t* task_offsets, int32_t* task_seg, int64_t max_tasks, cudaStream_t stream) {
     // S+1 segments: the superpoints plus the trash segment [seg_offsets[S], seg_offsets[S+1])
     const int32_t nseg = (int32_t)S + 1;
     size_t smem = 0;
-    if (anchor != nullptr && nseg <= kMaxOrderedSegs) {
+    if (xyz != nullptr && nseg <= kMaxOrderedSegs) {
         int n2 = 1;
         while (n2 < nseg) n2 <<= 1;
         smem = (size_t)(nseg <= kMaxRankedSegs ? 2 * kMaxRankedSegs : n2) * sizeof(uint64_t);
@@ -522,7 +697,7 @@ static int run_tasks(const int32_t* seg_offsets, const uint32_t* anchor, int64_t
                                           kMaxOrderedSegs * (int)sizeof(uint64_t), &attr, "sd3d_sp_tasks");
         if (rc != SD3D_OK) return rc;
     }
-    sp_tasks_kernel<<<1, 1024, smem, stream>>>(seg_offsets, anchor, nseg, run, task_offsets, task_seg, max_tasks);
+    sp_tasks_kernel<<<1, 1024, smem, stream>>>(seg_offsets, perm, xyz, nseg, run, task_offsets, task_seg, max_tasks);
     return SD3D_OK;
 }
 
@@ -580,7 +755,7 @@ extern "C" int sd3d_sp_tasks(const int32_t* seg_offsets, int64_t S, int run, int
         set_error("sd3d_sp_tasks: bad argument");
         return SD3D_ERR_ARG;
     }
-    const int rc = run_tasks(seg_offsets, nullptr, S, run, task_offsets, task_seg, max_tasks, stream);
+    const int rc = run_tasks(seg_offsets, nullptr, nullptr, S, run, task_offsets, task_seg, max_tasks, stream);
     if (rc != SD3D_OK) return rc;
     return check_launch("sd3d_sp_tasks");
 }
@@ -600,14 +775,14 @@ extern "C" int sd3d_sp_plan(const int64_t* idx, const float* xyz, int64_t N, int
     sort_ws_layout(N, S, ws, &w);
     if (N == 0) {
         cudaMemsetAsync(seg_offsets, 0, (size_t)(S + 2) * sizeof(int32_t), stream);
-        rc = run_tasks(seg_offsets, nullptr, S, run, task_offsets, task_seg, max_tasks, stream);
+        rc = run_tasks(seg_offsets, nullptr, nullptr, S, run, task_offsets, task_seg, max_tasks, stream);
         if (rc != SD3D_OK) return rc;
         return check_launch("sd3d_sp_plan(empty)");
     }
     rc = run_sort(idx, xyz, 1.0f / cell, N, S, perm, seg_offsets, w, stream);
     if (rc != SD3D_OK) return rc;
-    sp_refine_kernel<<<(unsigned)(S + 1), kSortThreads, 0, stream>>>(xyz, perm, w.cell, seg_offsets, order, w.anchor);
-    rc = run_tasks(seg_offsets, w.anchor, S, run, task_offsets, task_seg, max_tasks, stream);
+    rc = run_tasks(seg_offsets, perm, xyz, S, run, task_offsets, task_seg, max_tasks, stream);
     if (rc != SD3D_OK) return rc;
+    sp_refine_kernel<<<(unsigned)(S + 1), kSortThreads, 0, stream>>>(xyz, perm, w.cell, seg_offsets, order);
     return check_launch("sd3d_sp_plan");
 }

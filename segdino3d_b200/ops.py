@@ -220,6 +220,64 @@ def _check_lift_inputs(xyz, K, w2c, depth, fmap):
         raise ValueError("fmap must be channels-last [V,Hf,Wf,C] float32/float16/bfloat16")
 
 
+class _LiftLaunch:
+    """Validated arguments + output / workspace buffers of one ``sd3d_lift`` invocation (one scale)."""
+
+    def __init__(self, xyz, K, w2c, depth, fmap, stride, tau, z_near, views, finalize, pool, want_maps,
+                 accumulate_into, variant, n_segments, max_tasks, run):
+        _check_lift_inputs(xyz, K, w2c, depth, fmap)
+        self.xyz, self.K, self.w2c, self.depth, self.fmap = (t.contiguous() for t in (xyz, K, w2c, depth, fmap))
+        self.n, self.v = xyz.shape[0], K.shape[0]
+        self.hd, self.wd = depth.shape[1], depth.shape[2]
+        self.hf, self.wf, self.c = fmap.shape[1], fmap.shape[2], fmap.shape[3]
+        self.stride = float(self.wd / self.wf if stride is None else stride)
+        self.vb, self.ve = (0, self.v) if views is None else (int(views[0]), int(views[1]))
+        self.tau, self.z_near, self.finalize, self.pool, self.variant = float(tau), float(z_near), finalize, pool, int(variant)
+        self.s, self.max_tasks, self.run = int(n_segments), int(max_tasks), int(run)
+        self.accumulate = accumulate_into is not None
+        self.lib = _lib.load()
+        dev = self.dev = xyz.device
+        n, c, v = self.n, self.c, self.v
+        with torch.cuda.device(dev):
+            if accumulate_into is not None:
+                self.feat, self.count = accumulate_into
+                if (self.feat.dtype != torch.float32 or tuple(self.feat.shape) != (n, c) or not self.feat.is_contiguous()
+                        or self.count.dtype != torch.int32 or self.count.numel() != n or not self.count.is_contiguous()):
+                    raise ValueError("accumulate_into must be (float32 [N,C], int32 [N]) contiguous")
+            else:
+                self.feat = torch.empty(n, c, dtype=torch.float32, device=dev)
+                self.count = torch.empty(n, dtype=torch.int32, device=dev)
+            self.pix = self.vis = None
+            if want_maps:
+                self.pix = torch.full((v, n), -1, dtype=torch.int32, device=dev)
+                self.vis = torch.zeros((v, n), dtype=torch.uint8, device=dev)
+            self.sp_out = torch.empty(self.s, c, dtype=torch.float32, device=dev) if pool else None
+            self.ws_bytes = int(self.lib.sd3d_lift_workspace_bytes(n, self.ve - self.vb, c, self.max_tasks if pool else 0))
+            self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev)
+
+    def call(self, stage_bits: int, plan: Optional[SuperpointPlan]) -> None:
+        """stage_bits: 0 = projection + gather, 256 = projection only, 512 = gather only."""
+        with torch.cuda.device(self.dev):
+            check(self.lib.sd3d_lift(
+                _ptr(self.xyz), self.n, _ptr(self.K), _ptr(self.w2c), self.v, self.vb, self.ve, _ptr(self.depth),
+                _DEPTH_CODE[self.depth.dtype], self.hd, self.wd, _ptr(self.fmap), _FMAP_CODE[self.fmap.dtype], self.hf,
+                self.wf, self.c, self.stride, self.tau, self.z_near, 1 if self.accumulate else 0,
+                1 if self.finalize else 0, _ptr(plan.order) if plan is not None else None, _ptr(self.feat),
+                _ptr(self.count), _ptr(self.pix), _ptr(self.vis), _ptr(plan.seg_offsets) if plan is not None else None,
+                self.s, _ptr(plan.task_offsets) if plan is not None else None,
+                _ptr(plan.task_seg) if plan is not None else None, self.max_tasks,
+                self.run, _ptr(self.ws), self.ws_bytes, 1 if self.pool else 0, self.variant | stage_bits, _stream()),
+                "sd3d_lift")
+
+    def combine(self, plan: SuperpointPlan) -> None:
+        with torch.cuda.device(self.dev):
+            check(self.lib.sd3d_sp_combine(_ptr(self.ws), _ptr(plan.task_offsets), _ptr(plan.seg_offsets), self.s, self.c,
+                                           self.run, _ptr(self.sp_out), _stream()), "sd3d_sp_combine")
+
+    def result(self):
+        return {"feat": self.feat, "count": self.count, "pix_idx": self.pix, "vis": self.vis, "sp_feat": self.sp_out}
+
+
 def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Tensor, fmap: torch.Tensor,
          stride: Optional[float] = None, *, tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT,
          views: Optional[Tuple[int, int]] = None, finalize: bool = True, plan: Optional[SuperpointPlan] = None,
@@ -230,65 +288,25 @@ def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Ten
     Returns a dict with ``feat`` [N,C] (mean over visible views if ``finalize`` else the raw sum),
     ``count`` [N] int32 and, on request, ``pix_idx`` / ``vis`` [V,N] and ``sp_feat`` [S,C] (``pool=True`` needs
     ``plan``; the plan's permutation is also used as the cache-friendly processing order).
-    ``events`` (bench only): a pair of CUDA events recorded immediately before / after the lift kernel.
+    ``events`` (bench only): a pair of CUDA events recorded immediately before / after the gather kernel.
     """
-    _check_lift_inputs(xyz, K, w2c, depth, fmap)
-    xyz, K, w2c, depth, fmap = (t.contiguous() for t in (xyz, K, w2c, depth, fmap))
-    n, v = xyz.shape[0], K.shape[0]
-    hd, wd = depth.shape[1], depth.shape[2]
-    hf, wf, c = fmap.shape[1], fmap.shape[2], fmap.shape[3]
-    if stride is None:
-        stride = wd / wf
-    vb, ve = (0, v) if views is None else (int(views[0]), int(views[1]))
-    dev = xyz.device
-    lib = _lib.load()
     if pool and plan is None:
         raise ValueError("pool=True needs a SuperpointPlan (sp_sort)")
-    if plan is not None and plan.n_points != n:
+    if plan is not None and plan.n_points != xyz.shape[0]:
         raise ValueError("plan was built for a different number of points")
-    with torch.cuda.device(dev):
-        if accumulate_into is not None:
-            feat, count = accumulate_into
-            if (feat.dtype != torch.float32 or tuple(feat.shape) != (n, c) or not feat.is_contiguous()
-                    or count.dtype != torch.int32 or count.numel() != n or not count.is_contiguous()):
-                raise ValueError("accumulate_into must be (float32 [N,C], int32 [N]) contiguous")
-        else:
-            feat = torch.empty(n, c, dtype=torch.float32, device=dev)
-            count = torch.empty(n, dtype=torch.int32, device=dev)
-        pix = vis = None
-        if want_maps:
-            pix = torch.full((v, n), -1, dtype=torch.int32, device=dev)
-            vis = torch.zeros((v, n), dtype=torch.uint8, device=dev)
-        sp_out = None
-        s = 0
-        if plan is not None:
-            s = plan.n_segments
-        if pool:
-            sp_out = torch.empty(s, c, dtype=torch.float32, device=dev)
-        ws_bytes = int(lib.sd3d_lift_workspace_bytes(n, ve - vb, c, plan.max_tasks if pool else 0))
-        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-        def call(stage_bits):
-            check(lib.sd3d_lift(_ptr(xyz), n, _ptr(K), _ptr(w2c), v, vb, ve, _ptr(depth), _DEPTH_CODE[depth.dtype], hd, wd,
-                                _ptr(fmap), _FMAP_CODE[fmap.dtype], hf, wf, c, float(stride), float(tau), float(z_near),
-                                1 if accumulate_into is not None else 0, 1 if finalize else 0,
-                                _ptr(plan.order) if plan is not None else None, _ptr(feat), _ptr(count), _ptr(pix),
-                                _ptr(vis), _ptr(plan.seg_offsets) if plan is not None else None, s,
-                                _ptr(plan.task_offsets) if plan is not None else None,
-                                _ptr(plan.task_seg) if plan is not None else None,
-                                plan.max_tasks if plan is not None else 0, plan.run if plan is not None else DEFAULT_RUN,
-                                _ptr(ws), ws_bytes, 1 if pool else 0, int(variant) | stage_bits, _stream()), "sd3d_lift")
-
-        if events is None:
-            call(0)
-        else:  # bench only: bracket the gather kernel alone
-            call(256)
-            events[0].record()
-            call(512)
-            events[1].record()
-        if pool:
-            check(lib.sd3d_sp_combine(_ptr(ws), _ptr(plan.task_offsets), _ptr(plan.seg_offsets), s, c, plan.run,
-                                      _ptr(sp_out), _stream()), "sd3d_sp_combine")
-    return {"feat": feat, "count": count, "pix_idx": pix, "vis": vis, "sp_feat": sp_out}
+    L = _LiftLaunch(xyz, K, w2c, depth, fmap, stride, tau, z_near, views, finalize, pool, want_maps, accumulate_into,
+                    variant, plan.n_segments if plan is not None else 0, plan.max_tasks if plan is not None else 0,
+                    plan.run if plan is not None else DEFAULT_RUN)
+    if events is None:
+        L.call(0, plan)
+    else:  # bench only: bracket the gather kernel alone
+        L.call(256, plan)
+        events[0].record()
+        L.call(512, plan)
+        events[1].record()
+    if pool:
+        L.combine(plan)
+    return L.result()
 
 
 def lift_finalize(sum_inout: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
@@ -333,14 +351,54 @@ def scale_mean(feats: Sequence[torch.Tensor]) -> torch.Tensor:
     return out
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev: torch.device) -> torch.cuda.Stream:
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return st
+
+
 def lift_and_pool(xyz, K, pose_w2c, depth, fmap, sp_ids: torch.Tensor, n_superpoints: Optional[int] = None, *,
                   stride: Optional[float] = None, tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT,
-                  run: int = DEFAULT_RUN, variant: int = 0):
-    """The whole hot path for one scene: sort by superpoint -> fused lift + mean + superpoint pooling.
-    Returns (points_2dfeats [N,C], count [N], sp_feats [S,C], plan)."""
-    plan = sp_sort(sp_ids, n_superpoints, run=run, xyz=xyz)
-    r = lift(xyz, K, pose_w2c, depth, fmap, stride, tau=tau, z_near=z_near, plan=plan, pool=True, variant=variant)
-    return r["feat"], r["count"], r["sp_feat"], plan
+                  run: int = DEFAULT_RUN, variant: int = 0, overlap: bool = True,
+                  events: Optional[Tuple[torch.cuda.Event, torch.cuda.Event]] = None):
+    """The whole hot path for one scene: plan (sort by superpoint + spatial refinement + run table), projection,
+    gather + mean + run partials, ordered combine. Returns (points_2dfeats [N,C], count [N], sp_feats [S,C], plan).
+
+    ``overlap``: the projection kernel needs no plan, so it is launched on a side stream and runs concurrently
+    with the (latency-bound) plan kernels; the gather waits for both."""
+    _need_cuda("sp_ids", sp_ids)
+    n = xyz.shape[0]
+    if n_superpoints is None:
+        n_superpoints = int(sp_ids.max().item()) + 1 if n > 0 else 0
+    max_tasks = int(_lib.load().sd3d_sp_max_tasks(n, int(n_superpoints), run))
+    L = _LiftLaunch(xyz, K, pose_w2c, depth, fmap, stride, tau, z_near, None, True, True, False, None, variant,
+                    n_superpoints, max_tasks, run)
+    if overlap and n > 0:
+        cur = torch.cuda.current_stream(L.dev)
+        side = _side_stream(L.dev)
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(cur)  # inputs and the buffers allocated above are ready for the side stream
+        with torch.cuda.stream(side):
+            side.wait_event(fork)
+            L.call(256, None)  # projection in input order
+            join.record(side)
+        plan = sp_sort(sp_ids, n_superpoints, run=run, xyz=L.xyz)
+        cur.wait_event(join)
+    else:
+        plan = sp_sort(sp_ids, n_superpoints, run=run, xyz=L.xyz)
+        L.call(256, plan)
+    if events is not None:
+        events[0].record()
+    L.call(512, plan)
+    if events is not None:
+        events[1].record()
+    L.combine(plan)
+    return L.feat, L.count, L.sp_out, plan
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -44,11 +44,11 @@ class ScenePipeline:
     scenes have been yielded (copy them if they must outlive that)."""
 
     def __init__(self, device: torch.device, depth: int = 3, run: int = ops.DEFAULT_RUN, variant: int = 0,
-                 tau: float = ops.TAU_DEFAULT, z_near: float = ops.Z_NEAR_DEFAULT, refine: bool = True):
+                 tau: float = ops.TAU_DEFAULT, z_near: float = ops.Z_NEAR_DEFAULT):
         if torch.device(device).type != "cuda":
             raise ops.Sd3dError("ScenePipeline needs a CUDA device (no CPU fallback)")
         self.device = torch.device(device)
-        self.depth, self.run_len, self.variant, self.tau, self.z_near, self.refine = depth, run, variant, tau, z_near, refine
+        self.depth, self.run_len, self.variant, self.tau, self.z_near = depth, run, variant, tau, z_near
         with torch.cuda.device(self.device):
             self.s_in = torch.cuda.Stream()
             self.s_comp = torch.cuda.Stream()
@@ -80,10 +80,10 @@ class ScenePipeline:
         with torch.cuda.stream(self.s_comp):
             self.s_comp.wait_event(slot.ev_h2d)
             self.s_comp.wait_event(slot.ev_d2h)  # the previous outputs of this slot have left the device
-            plan = ops.sp_sort(d["sp_ids"], n_sp, run=self.run_len, xyz=d["xyz"] if self.refine else None)
-            r = ops.lift(d["xyz"], d["K"], d["w2c"], d["depth"], d["fmap"], stride, tau=self.tau, z_near=self.z_near,
-                         plan=plan, pool=True, variant=self.variant)
-            slot.out_dev = (r["feat"], r["count"], r["sp_feat"], plan)
+            feat, count, sp, plan = ops.lift_and_pool(d["xyz"], d["K"], d["w2c"], d["depth"], d["fmap"], d["sp_ids"], n_sp,
+                                                      stride=stride, tau=self.tau, z_near=self.z_near, run=self.run_len,
+                                                      variant=self.variant, overlap=True)
+            slot.out_dev = (feat, count, sp, plan)
             slot.ev_comp.record(self.s_comp)
 
     def _stage_out(self, slot: _Slot) -> None:
