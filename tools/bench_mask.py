@@ -1,0 +1,37 @@
+"""Mask-logit GEMM timings (a-5): tcgen05 bf16 kernel, fp32 FFMA kernel, torch.einsum (cuBLAS fp32, the
+reference's path) at the ScanNet200 decoder shape, the eval shape (n = S) and a large shape. One JSON line each."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import segdino3d_b200 as sd
+from segdino3d_b200.synth import make_decoder_operands
+
+dev = "cuda:0"
+PEAK_TF = 1645.7
+try:
+    PEAK_TF = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["bf16_tflops"]
+except Exception:
+    pass
+
+def timeit(fn, iters=200):
+    for _ in range(10): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e-3
+
+for (n, s, d) in [(200, 500, 256), (500, 500, 256), (5000, 5000, 256)]:
+    q, mf = make_decoder_operands(n, s, d)
+    q, mf = q.to(dev), mf.to(dev)
+    flop = 2.0 * n * s * d
+    res = {"shape": [n, s, d], "flop": flop}
+    for name, fn in (("tcgen05_bf16", lambda: sd.mask_logits(q, mf, precision="bf16")),
+                     ("tcgen05_bf16+attn_mask", lambda: sd.mask_logits(q, mf, precision="bf16", threshold=0.5)),
+                     ("ffma_fp32", lambda: sd.mask_logits(q, mf, precision="fp32")),
+                     ("torch_einsum_fp32", lambda: torch.einsum("nd,md->nm", q, mf)),
+                     ("torch_einsum+mask_epilogue", lambda: (lambda pm: ((pm.sigmoid() < 0.5), pm))(torch.einsum("nd,md->nm", q, mf)))):
+        t = timeit(fn, 50 if n >= 5000 else 200)
+        res[name] = {"us": t * 1e6, "tflops": flop / t / 1e12, "frac_of_bf16_peak": flop / t / 1e12 / PEAK_TF}
+    print(json.dumps(res), flush=True)
