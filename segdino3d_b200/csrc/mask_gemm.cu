@@ -14,6 +14,8 @@
 //               accumulator in TMEM, tcgen05.commit signals an mbarrier, and the four warps read their
 //               32 TMEM lanes back with tcgen05.ld for the epilogue (logits + sigmoid threshold).
 // Tensor-pipe roofline note: 2*n*S*d = 51 MFLOP at the ScanNet200 shape -> launch/latency bound; see DESIGN.md.
+#include <cmath>
+
 #include "common.cuh"
 
 namespace sd3d {
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN))
             if (gn >= S) continue;
             const float v = acc[i][j];
             out[(int64_t)gm * S + gn] = v;
-            if (attn) attn[(int64_t)gm * S + gn] = (1.0f / (1.0f + expf(-v))) < thr ? 1 : 0;
+            if (attn) attn[(int64_t)gm * S + gn] = v < thr ? 1 : 0;  // thr is already a logit
         }
     }
 }
@@ -241,13 +243,32 @@ __global__ void __launch_bounds__(kTcThreads)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (gm < n) {
+            float* orow = out + (int64_t)gm * S + n0 + c0;
+            const bool full = (n0 + c0 + 32 <= S);
+            if (full && (S & 3) == 0) {  // 16-byte aligned row chunks: 128-bit stores
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int gn = n0 + c0 + j;
-                if (gn < S) {
-                    const float val = __uint_as_float(v[j]);
-                    out[(int64_t)gm * S + gn] = val;
-                    if (attn) attn[(int64_t)gm * S + gn] = (1.0f / (1.0f + expf(-val))) < thr ? 1 : 0;
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4*>(orow + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                if (attn) {
+                    uint32_t* arow = reinterpret_cast<uint32_t*>(attn + (int64_t)gm * S + n0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        uint32_t w = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) w |= (__uint_as_float(v[j + k]) < thr ? 1u : 0u) << (8 * k);
+                        arow[j >> 2] = w;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int gn = n0 + c0 + j;
+                    if (gn < S) {
+                        const float val = __uint_as_float(v[j]);
+                        out[(int64_t)gm * S + gn] = val;
+                        if (attn) attn[(int64_t)gm * S + gn] = val < thr ? 1 : 0;  // thr is already a logit
+                    }
                 }
             }
         }
@@ -272,6 +293,11 @@ extern "C" int sd3d_mask_logits(const float* q, const float* mf, int n, int S, i
         return SD3D_ERR_ARG;
     }
     if (n == 0 || S == 0) return SD3D_OK;
+    // sigmoid(x) < thr  <=>  x < logit(thr): the epilogue compares logits (no expf per element)
+    if (attn_mask != nullptr) {
+        const double t = (double)thr;
+        thr = t <= 0.0 ? -INFINITY : (t >= 1.0 ? INFINITY : (float)log(t / (1.0 - t)));
+    }
     if (q == nullptr || mf == nullptr || out == nullptr) {
         set_error("sd3d_mask_logits: null buffer");
         return SD3D_ERR_ARG;
