@@ -143,6 +143,24 @@ int sd3d_scale_mean(const float* const* feats_host /*host array of L device ptrs
 int sd3d_mask_logits(const float* q, const float* mf, int n, int S, int d, int precision, float* out,
                      float thr, uint8_t* attn_mask, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * "next" rows of SURVEY 8(f)
+ * --------------------------------------------------------------------------------------------- */
+
+/* Superpoint -> point mask expansion with threshold and per-instance point count, one pass:
+ *   mask_pred = mask_pred_sigmoid[:, superpoints] > thr ; mask_pointnum = mask_pred.sum(1)
+ *   segdino3d/models/architecture/baseline3d.py:453-454,463.
+ * mask_sig[K,S] f32 (already sigmoid / NMS-decayed, as at :453), superpoints[N] int64, out[K,N] u8 (0/1),
+ * pointnum[K] int32 (fully overwritten). Ids outside [0,S) expand to 0. */
+int sd3d_sp_expand_mask(const float* mask_sig, const int64_t* superpoints, int K, int64_t S, int64_t N, float thr,
+                        uint8_t* out, int32_t* pointnum, void* stream);
+
+/* Gradient of scatter_mean(src, idx, dim=0) w.r.t. src: grad_src[p,:] = grad_out[idx[p],:] / max(|idx[p]|,1)
+ *   (the pooling runs under autograd in training: engine/train_engine_3d.py:99-105, spconvunet.py:390).
+ * seg_offsets from sd3d_sp_sort (superpoint sizes); ids outside [0,S) get zero gradient. */
+int sd3d_sp_mean_backward(const float* grad_out, const int64_t* idx, const int32_t* seg_offsets, int64_t N, int64_t S,
+                          int C, float* grad_src, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,8 +4,10 @@ pooling and mask-logit path, behind the reference's own operator interface. See 
 Importing the package does not load the CUDA library; the first op call does, and raises if
 libsd3d.so is missing (there is no CPU fallback)."""
 from ._lib import Sd3dError  # noqa: F401
-from .ops import (SuperpointPlan, lift, lift_and_pool, lift_features, lift_finalize, mask_logits,  # noqa: F401
-                  scale_mean, scatter_mean, sp_mean, sp_sort)
+from .io import load_points_2dfeats, save_points_2dfeats  # noqa: F401
+from .ops import (SuperpointPlan, expand_superpoint_masks, lift, lift_and_pool, lift_features,  # noqa: F401
+                  lift_finalize, mask_logits, scale_mean, scatter_mean, sp_mean, sp_sort)
 
-__all__ = ["Sd3dError", "SuperpointPlan", "lift", "lift_and_pool", "lift_features", "lift_finalize", "mask_logits",
-           "scale_mean", "scatter_mean", "sp_mean", "sp_sort"]
+__all__ = ["Sd3dError", "SuperpointPlan", "expand_superpoint_masks", "lift", "lift_and_pool", "lift_features",
+           "lift_finalize", "load_points_2dfeats", "mask_logits", "save_points_2dfeats", "scale_mean", "scatter_mean",
+           "sp_mean", "sp_sort"]

@@ -1,0 +1,166 @@
+// sp_expand.cu -- rows "next" of SURVEY.md section 8(f): superpoint -> point mask expansion, and the backward
+// of the superpoint mean.
+//
+// (1) sd3d_sp_expand_mask replaces, in Baseline3D.predict_by_feat_instance
+//     (/root/reference/segdino3d/models/architecture/baseline3d.py:453-454, :463),
+//         mask_pred_sigmoid = mask_pred_sigmoid[:, superpoints]          # [K,S] -> [K,N] fp32 gather (240 MB at K=600)
+//         mask_pred = mask_pred_sigmoid > self.test_cfg.sp_score_thr
+//         mask_pointnum = mask_pred.sum(1)
+//     with ONE pass that never materialises the fp32 [K,N] tensor: the comparison is done per superpoint, the
+//     boolean row is expanded with 128-bit stores, the per-instance point count is accumulated with integer
+//     atomics (exact). Write-bound: K*N bytes out, N*8 bytes of ids in (once per 32 rows).
+// (2) sd3d_sp_mean_backward: grad_src[p,:] = grad_out[idx[p],:] / max(|idx[p]|,1), the gradient of
+//     scatter_mean(src, idx, dim=0) (spconvunet.py:390 is called under autograd in training,
+//     engine/train_engine_3d.py:99-105). Read N*8 + S*C*4 (L2 resident), write N*C*4.
+#include "common.cuh"
+
+namespace sd3d {
+
+constexpr int kExpThreads = 256;
+constexpr int kExpPtsPerThread = 16;  // one 128-bit store of mask bytes
+constexpr int kExpRows = 32;          // instances per CTA: the ids are loaded once for 32 output rows
+
+__global__ void __launch_bounds__(kExpThreads)
+    sp_expand_mask_kernel(const float* __restrict__ mask_sig, const int64_t* __restrict__ superpoints, int K, int S,
+                          int64_t N, float thr, uint8_t* __restrict__ out, int32_t* __restrict__ pointnum) {
+    extern __shared__ uint8_t s_bits[];  // [kExpRows][S] : mask_sig[k,s] > thr
+    __shared__ int32_t s_cnt[kExpRows];
+    const int k0 = blockIdx.y * kExpRows;
+    const int rows = min(kExpRows, K - k0);
+    for (int i = threadIdx.x; i < rows * S; i += kExpThreads) {
+        const int r = i / S, s = i % S;
+        s_bits[r * S + s] = __ldg(mask_sig + (int64_t)(k0 + r) * S + s) > thr ? 1 : 0;
+    }
+    if (threadIdx.x < kExpRows) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t p0 = ((int64_t)blockIdx.x * kExpThreads + threadIdx.x) * kExpPtsPerThread;
+    int32_t ids[kExpPtsPerThread];
+#pragma unroll
+    for (int j = 0; j < kExpPtsPerThread; ++j) {
+        const int64_t p = p0 + j;
+        int64_t id = p < N ? __ldg(superpoints + p) : -1;
+        ids[j] = (id >= 0 && id < S) ? (int32_t)id : -1;  // ids outside [0,S) expand to False
+    }
+    const bool vec_ok = (p0 + kExpPtsPerThread <= N) && ((N & 15) == 0);
+    for (int r = 0; r < rows; ++r) {
+        const uint8_t* bits = s_bits + r * S;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < kExpPtsPerThread; ++j) {
+            const uint32_t b = ids[j] >= 0 ? bits[ids[j]] : 0u;
+            w[j >> 2] |= b << (8 * (j & 3));
+            c += (int)b;
+        }
+        uint8_t* dst = out + (int64_t)(k0 + r) * N + p0;
+        if (vec_ok) {
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kExpPtsPerThread; ++j)
+                if (p0 + j < N) dst[j] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 1u);
+        }
+        // warp-reduce the count, one smem atomic per warp, one global atomic per CTA row
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+        if (lane_id() == 0 && c) atomicAdd(&s_cnt[r], c);
+    }
+    __syncthreads();
+    if (threadIdx.x < rows && s_cnt[threadIdx.x]) atomicAdd(pointnum + k0 + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+// grad_src[p, :] = grad_out[idx[p], :] / max(n_idx[p], 1); seg sizes from seg_offsets (sd3d_sp_sort)
+__global__ void __launch_bounds__(256)
+    sp_mean_backward_kernel(const float* __restrict__ grad_out, const int64_t* __restrict__ idx,
+                            const int32_t* __restrict__ seg_offsets, int64_t N, int32_t S, int C,
+                            float* __restrict__ grad_src) {
+    const int vec_per_row = C >> 2;  // vectorised path: C % 4 == 0
+    const int64_t total = N * vec_per_row;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = g / vec_per_row;
+        const int c = (int)(g % vec_per_row) * 4;
+        const int64_t s = __ldg(idx + p);
+        float4 v = f4_zero();
+        if (s >= 0 && s < S) {
+            const float n = (float)max(__ldg(seg_offsets + s + 1) - __ldg(seg_offsets + s), 1);
+            v = f4_div(ldg_f4(grad_out + s * (int64_t)C + c), n);
+        }
+        st_cs_f4(grad_src + p * (int64_t)C + c, v);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+    sp_mean_backward_scalar_kernel(const float* __restrict__ grad_out, const int64_t* __restrict__ idx,
+                                   const int32_t* __restrict__ seg_offsets, int64_t N, int32_t S, int C,
+                                   float* __restrict__ grad_src) {
+    const int64_t total = N * C;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = g / C;
+        const int c = (int)(g % C);
+        const int64_t s = __ldg(idx + p);
+        float v = 0.f;
+        if (s >= 0 && s < S) {
+            const float n = (float)max(__ldg(seg_offsets + s + 1) - __ldg(seg_offsets + s), 1);
+            v = __fdiv_rn(__ldg(grad_out + s * (int64_t)C + c), n);
+        }
+        grad_src[g] = v;
+    }
+}
+
+}  // namespace sd3d
+
+using namespace sd3d;
+
+extern "C" int sd3d_sp_expand_mask(const float* mask_sig, const int64_t* superpoints, int K, int64_t S, int64_t N,
+                                   float thr, uint8_t* out, int32_t* pointnum, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (K < 0 || S < 0 || N < 0 || S > 200000) {
+        set_error("sd3d_sp_expand_mask: bad shape K=%d S=%lld N=%lld (S <= 200000)", K, (long long)S, (long long)N);
+        return SD3D_ERR_ARG;
+    }
+    if (K == 0) return SD3D_OK;
+    if (pointnum == nullptr || (N > 0 && (out == nullptr || superpoints == nullptr)) || (S > 0 && mask_sig == nullptr)) {
+        set_error("sd3d_sp_expand_mask: null buffer");
+        return SD3D_ERR_ARG;
+    }
+    cudaMemsetAsync(pointnum, 0, (size_t)K * sizeof(int32_t), stream);
+    if (N == 0) return check_launch("sd3d_sp_expand_mask(empty)");
+    const size_t smem = (size_t)kExpRows * (size_t)(S > 0 ? S : 1);
+    if (smem > 200 * 1024) {
+        set_error("sd3d_sp_expand_mask: S=%lld too large for the shared-memory mask tile", (long long)S);
+        return SD3D_ERR_UNSUPPORTED;
+    }
+    if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(sp_expand_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   200 * 1024);
+        if (e != cudaSuccess) {
+            set_error("sd3d_sp_expand_mask: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return SD3D_ERR_CUDA;
+        }
+    }
+    dim3 grid((unsigned)ceil_div64(N, (int64_t)kExpThreads * kExpPtsPerThread), (unsigned)((K + kExpRows - 1) / kExpRows));
+    sp_expand_mask_kernel<<<grid, kExpThreads, smem, stream>>>(mask_sig, superpoints, K, (int)S, N, thr, out, pointnum);
+    return check_launch("sd3d_sp_expand_mask");
+}
+
+extern "C" int sd3d_sp_mean_backward(const float* grad_out, const int64_t* idx, const int32_t* seg_offsets, int64_t N,
+                                     int64_t S, int C, float* grad_src, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (N < 0 || S < 0 || C <= 0 || S >= (int64_t(1) << 30)) {
+        set_error("sd3d_sp_mean_backward: bad shape N=%lld S=%lld C=%d", (long long)N, (long long)S, C);
+        return SD3D_ERR_ARG;
+    }
+    if (N == 0) return SD3D_OK;
+    if (idx == nullptr || seg_offsets == nullptr || grad_src == nullptr || (S > 0 && grad_out == nullptr)) {
+        set_error("sd3d_sp_mean_backward: null buffer");
+        return SD3D_ERR_ARG;
+    }
+    const bool vec = (C % 4 == 0) && aligned16(grad_out) && aligned16(grad_src);
+    const int64_t total = vec ? N * (C / 4) : N * (int64_t)C;
+    const unsigned grid = (unsigned)imin64(ceil_div64(total, 256), (int64_t)num_sms() * 32);
+    if (vec)
+        sp_mean_backward_kernel<<<grid, 256, 0, stream>>>(grad_out, idx, seg_offsets, N, (int32_t)S, C, grad_src);
+    else
+        sp_mean_backward_scalar_kernel<<<grid, 256, 0, stream>>>(grad_out, idx, seg_offsets, N, (int32_t)S, C, grad_src);
+    return check_launch("sd3d_sp_mean_backward");
+}

@@ -186,19 +186,68 @@ def scatter_mean(src: torch.Tensor, index: torch.Tensor, dim: int = -1, out: Opt
         s = 0
     else:
         s = int(index.max().item()) + 1
-    plan = sp_sort(index, s)
-    res = sp_mean(src2, plan, exact=exact)
+    if src2.requires_grad and torch.is_grad_enabled():
+        res = _ScatterMeanFn.apply(src2, index, s, exact)
+        plan = None
+    else:
+        plan = sp_sort(index, s)
+        res = sp_mean(src2, plan, exact=exact)
     if orig_dtype != torch.float32:
         res = res.to(orig_dtype)
     if squeeze:
         res = res.squeeze(1)
     if out is not None:
         # torch_scatter: out.scatter_add_(src) then out /= count  ==  (out + sum) / count
+        if plan is None:
+            plan = sp_sort(index, s)
         counts = (plan.seg_offsets[1:s + 1] - plan.seg_offsets[:s]).clamp(min=1).to(out.dtype)
         cshape = counts if out.dim() == 1 else counts[:, None]
         out.copy_(out / cshape + res)
         return out
     return res
+
+
+class _ScatterMeanFn(torch.autograd.Function):
+    """scatter_mean(src, index, dim=0) with the backward grad_src[p] = grad_out[index[p]] / max(|index[p]|, 1)."""
+
+    @staticmethod
+    def forward(ctx, src2, index, n_segments, exact):
+        plan = sp_sort(index, n_segments)
+        ctx.save_for_backward(index.contiguous(), plan.seg_offsets)
+        ctx.n_segments = n_segments
+        return sp_mean(src2, plan, exact=exact)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        index, seg_offsets = ctx.saved_tensors
+        grad_out = grad_out.contiguous().float()
+        n, c = index.numel(), grad_out.shape[1]
+        grad_src = torch.empty(n, c, dtype=torch.float32, device=grad_out.device)
+        with torch.cuda.device(grad_out.device):
+            check(_lib.load().sd3d_sp_mean_backward(_ptr(grad_out), _ptr(index), _ptr(seg_offsets), n, ctx.n_segments, c,
+                                                    _ptr(grad_src), _stream()), "sd3d_sp_mean_backward")
+        return grad_src, None, None, None
+
+
+def expand_superpoint_masks(mask_pred_sigmoid: torch.Tensor, superpoints: torch.Tensor, sp_score_thr: float):
+    """``mask_pred = mask_pred_sigmoid[:, superpoints] > sp_score_thr`` and ``mask_pred.sum(1)`` in one pass
+    (Baseline3D.predict_by_feat_instance, models/architecture/baseline3d.py:453-454,463) without materialising the
+    fp32 ``[K, N]`` tensor. Returns (mask_pred bool [K,N], mask_pointnum int64 [K])."""
+    _need_cuda("mask_pred_sigmoid", mask_pred_sigmoid)
+    _need_cuda("superpoints", superpoints)
+    if mask_pred_sigmoid.dim() != 2 or superpoints.dim() != 1:
+        raise ValueError("expected mask_pred_sigmoid [K,S] and superpoints [N]")
+    m = mask_pred_sigmoid.float().contiguous()
+    sp = superpoints.to(torch.int64).contiguous()
+    k, s = m.shape
+    n = sp.numel()
+    dev = m.device
+    with torch.cuda.device(dev):
+        out = torch.empty(k, n, dtype=torch.uint8, device=dev)
+        pointnum = torch.empty(k, dtype=torch.int32, device=dev)
+        check(_lib.load().sd3d_sp_expand_mask(_ptr(m), _ptr(sp), k, s, n, float(sp_score_thr), _ptr(out), _ptr(pointnum),
+                                              _stream()), "sd3d_sp_expand_mask")
+    return out.view(torch.bool), pointnum.long()
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -80,3 +80,18 @@ def test_batch_superpoint_ids_matches_reference_pattern():
     ids2, offs2 = so.batch_superpoint_ids_oracle(sps)
     assert torch.equal(ids, ids2) and offs == offs2
     assert sps[0].tolist() == [0, 2, 2, 1]  # inputs are cloned, not mutated (spconvunet.py:369)
+
+
+def test_pth_wire_format_round_trip(tmp_path):
+    """features_2d/{scene}.pth is a python list over scales of [N,C] float32 CPU tensors; the loader
+    stacks and averages them (scannet200.py:224,233-234)."""
+    g = torch.Generator().manual_seed(0)
+    feats = [torch.randn(50, 256, generator=g), torch.randn(50, 256, generator=g).double()]
+    path = sd.save_points_2dfeats(str(tmp_path / "features_2d"), "scene0000_00", feats)
+    raw = torch.load(path)
+    assert isinstance(raw, list) and len(raw) == 2
+    assert all(t.dtype == torch.float32 and t.device.type == "cpu" and t.shape == (50, 256) for t in raw)
+    fused = sd.load_points_2dfeats(str(tmp_path / "features_2d"), "scene0000_00")
+    assert torch.equal(fused, torch.stack([feats[0], feats[1].float()], 0).mean(0))
+    with pytest.raises(ValueError):
+        sd.save_points_2dfeats(str(tmp_path), "bad", [torch.zeros(3, 4), torch.zeros(4, 4)])

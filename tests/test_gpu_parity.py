@@ -424,3 +424,45 @@ def test_forward_head_masks(precision):
     assert not am.any()
     pred2, attn2 = plugin.forward_head_masks([qs[0].to(DEV)], [mfs[0].to(DEV)], None, precision=precision)
     assert attn2 is None and torch.equal(pred2[0], pred[0])
+
+
+# ----------------------------------------------------------------------------------------------------
+# "next" rows of SURVEY 8(f)
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("k,s,n", [(600, 500, 100_000), (7, 33, 1001), (1, 1, 16), (40, 3000, 50_000)])
+def test_expand_superpoint_masks(k, s, n):
+    """mask_pred_sigmoid[:, superpoints] > thr and its row sums (baseline3d.py:453-454,463): exact."""
+    g = torch.Generator().manual_seed(k + s)
+    m = torch.rand(k, s, generator=g)
+    sp = torch.randint(0, s, (n,), generator=g)
+    want = m[:, sp] > 0.35
+    got, cnt = sd.expand_superpoint_masks(m.to(DEV), sp.to(DEV), 0.35)
+    assert got.dtype == torch.bool and got.shape == (k, n)
+    assert torch.equal(got.cpu(), want) and torch.equal(cnt.cpu(), want.sum(1))
+
+
+def test_scatter_mean_backward_matches_autograd():
+    g = torch.Generator().manual_seed(4)
+    for n, s, c in [(5000, 60, 32), (3000, 17, 3), (2000, 40, 96)]:
+        src = torch.randn(n, c, generator=g)
+        idx = torch.randint(0, s, (n,), generator=g)
+        w = torch.randn(s, c, generator=g)
+        ref = src.clone().requires_grad_(True)
+        (so.scatter_mean_oracle(ref, idx, dim=0, dim_size=s) * w).sum().backward()
+        x = src.to(DEV).requires_grad_(True)
+        out = sd.scatter_mean(x, idx.to(DEV), dim=0, dim_size=s)
+        assert torch.equal(out.detach().cpu(), so.scatter_mean_oracle(src, idx, dim=0, dim_size=s))
+        (out * w.to(DEV)).sum().backward()
+        assert torch.allclose(x.grad.cpu(), ref.grad, rtol=1e-6, atol=1e-7)
+
+
+def test_pth_producer_feeds_the_reference_loader(tmp_path, small_scene):
+    """lift_features -> features_2d/{scene}.pth -> the loader's stack().mean(0) == oracle (scannet200.py:219-234)."""
+    sc = small_scene
+    fm2 = torch.randn(sc.K.shape[0], sc.depth.shape[1] // 8, sc.depth.shape[2] // 8, 64,
+                      generator=torch.Generator().manual_seed(3))
+    feats = sd.lift_features(sc.xyz.to(DEV), sc.K.to(DEV), sc.w2c.to(DEV), sc.depth.to(DEV), [sc.fmap.to(DEV), fm2.to(DEV)])
+    sd.save_points_2dfeats(str(tmp_path), "scene0001_00", feats)
+    loaded = sd.load_points_2dfeats(str(tmp_path), "scene0001_00")
+    want = lo.scale_mean_oracle(lo.lift_features_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, [sc.fmap, fm2]))
+    assert torch.equal(loaded, want)
