@@ -23,47 +23,50 @@ constexpr int kExpRows = 32;          // instances per CTA: the ids are loaded o
 __global__ void __launch_bounds__(kExpThreads)
     sp_expand_mask_kernel(const float* __restrict__ mask_sig, const int64_t* __restrict__ superpoints, int K, int S,
                           int64_t N, float thr, uint8_t* __restrict__ out, int32_t* __restrict__ pointnum) {
-    extern __shared__ uint8_t s_bits[];  // [kExpRows][S] : mask_sig[k,s] > thr
+    // s_word[s] bit r = (mask_sig[k0+r, s] > thr): ONE shared-memory lookup per point yields the bits of all
+    // 32 instance rows this CTA writes
+    extern __shared__ uint32_t s_word[];
     __shared__ int32_t s_cnt[kExpRows];
     const int k0 = blockIdx.y * kExpRows;
     const int rows = min(kExpRows, K - k0);
-    for (int i = threadIdx.x; i < rows * S; i += kExpThreads) {
-        const int r = i / S, s = i % S;
-        s_bits[r * S + s] = __ldg(mask_sig + (int64_t)(k0 + r) * S + s) > thr ? 1 : 0;
+    for (int s = threadIdx.x; s < S; s += kExpThreads) {
+        uint32_t w = 0u;
+        for (int r = 0; r < rows; ++r) w |= (__ldg(mask_sig + (int64_t)(k0 + r) * S + s) > thr ? 1u : 0u) << r;
+        s_word[s] = w;
     }
     if (threadIdx.x < kExpRows) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const int64_t p0 = ((int64_t)blockIdx.x * kExpThreads + threadIdx.x) * kExpPtsPerThread;
-    int32_t ids[kExpPtsPerThread];
+    const int64_t n_chunks = ceil_div64(N, (int64_t)kExpThreads * kExpPtsPerThread);
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {  // the word table is built once per CTA
+    const int64_t p0 = (chunk * kExpThreads + threadIdx.x) * kExpPtsPerThread;
+    uint32_t pw[kExpPtsPerThread];
 #pragma unroll
     for (int j = 0; j < kExpPtsPerThread; ++j) {
         const int64_t p = p0 + j;
-        int64_t id = p < N ? __ldg(superpoints + p) : -1;
-        ids[j] = (id >= 0 && id < S) ? (int32_t)id : -1;  // ids outside [0,S) expand to False
+        const int64_t id = p < N ? __ldg(superpoints + p) : -1;
+        pw[j] = (id >= 0 && id < S) ? s_word[id] : 0u;  // ids outside [0,S) expand to False
     }
     const bool vec_ok = (p0 + kExpPtsPerThread <= N) && ((N & 15) == 0);
     for (int r = 0; r < rows; ++r) {
-        const uint8_t* bits = s_bits + r * S;
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         int c = 0;
 #pragma unroll
         for (int j = 0; j < kExpPtsPerThread; ++j) {
-            const uint32_t b = ids[j] >= 0 ? bits[ids[j]] : 0u;
+            const uint32_t b = (pw[j] >> r) & 1u;
             w[j >> 2] |= b << (8 * (j & 3));
             c += (int)b;
         }
         uint8_t* dst = out + (int64_t)(k0 + r) * N + p0;
         if (vec_ok) {
-            *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+            __stcs(reinterpret_cast<uint4*>(dst), make_uint4(w[0], w[1], w[2], w[3]));
         } else {
 #pragma unroll
             for (int j = 0; j < kExpPtsPerThread; ++j)
                 if (p0 + j < N) dst[j] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 1u);
         }
-        // warp-reduce the count, one smem atomic per warp, one global atomic per CTA row
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(kFull, c, o);
+        c = __reduce_add_sync(kFull, c);  // one REDUX per row, one smem atomic per warp
         if (lane_id() == 0 && c) atomicAdd(&s_cnt[r], c);
+    }
     }
     __syncthreads();
     if (threadIdx.x < rows && s_cnt[threadIdx.x]) atomicAdd(pointnum + k0 + threadIdx.x, s_cnt[threadIdx.x]);
@@ -114,8 +117,8 @@ using namespace sd3d;
 extern "C" int sd3d_sp_expand_mask(const float* mask_sig, const int64_t* superpoints, int K, int64_t S, int64_t N,
                                    float thr, uint8_t* out, int32_t* pointnum, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (K < 0 || S < 0 || N < 0 || S > 200000) {
-        set_error("sd3d_sp_expand_mask: bad shape K=%d S=%lld N=%lld (S <= 200000)", K, (long long)S, (long long)N);
+    if (K < 0 || S < 0 || N < 0 || S > 50000) {
+        set_error("sd3d_sp_expand_mask: bad shape K=%d S=%lld N=%lld (S <= 50000)", K, (long long)S, (long long)N);
         return SD3D_ERR_ARG;
     }
     if (K == 0) return SD3D_OK;
@@ -125,7 +128,7 @@ extern "C" int sd3d_sp_expand_mask(const float* mask_sig, const int64_t* superpo
     }
     cudaMemsetAsync(pointnum, 0, (size_t)K * sizeof(int32_t), stream);
     if (N == 0) return check_launch("sd3d_sp_expand_mask(empty)");
-    const size_t smem = (size_t)kExpRows * (size_t)(S > 0 ? S : 1);
+    const size_t smem = sizeof(uint32_t) * (size_t)(S > 0 ? S : 1);
     if (smem > 200 * 1024) {
         set_error("sd3d_sp_expand_mask: S=%lld too large for the shared-memory mask tile", (long long)S);
         return SD3D_ERR_UNSUPPORTED;
@@ -138,7 +141,11 @@ extern "C" int sd3d_sp_expand_mask(const float* mask_sig, const int64_t* superpo
             return SD3D_ERR_CUDA;
         }
     }
-    dim3 grid((unsigned)ceil_div64(N, (int64_t)kExpThreads * kExpPtsPerThread), (unsigned)((K + kExpRows - 1) / kExpRows));
+    const int64_t n_chunks = ceil_div64(N, (int64_t)kExpThreads * kExpPtsPerThread);
+    const int row_groups = (K + kExpRows - 1) / kExpRows;
+    // ~4 CTAs per SM in total: every CTA builds its 32-row word table once and then loops over point chunks
+    const int64_t gx = imin64(n_chunks, imax64(1, (int64_t)4 * num_sms() / row_groups));
+    dim3 grid((unsigned)gx, (unsigned)row_groups);
     sp_expand_mask_kernel<<<grid, kExpThreads, smem, stream>>>(mask_sig, superpoints, K, (int)S, N, thr, out, pointnum);
     return check_launch("sd3d_sp_expand_mask");
 }

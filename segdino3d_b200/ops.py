@@ -152,6 +152,27 @@ def sp_mean(src: torch.Tensor, plan: SuperpointPlan, exact: bool = True,
     return out
 
 
+_PLAN_CACHE: "dict" = {}
+
+
+def _cached_plan(index: torch.Tensor, s: int) -> SuperpointPlan:
+    """The reference pools several tensors with the SAME index back to back (features, DINO-X features,
+    coordinates: spconvunet.py:390,392,325): the sort is keyed on the index tensor's storage + version counter
+    and reused. (The key holds no reference to the tensor; a recycled address with equal version, length and
+    stream cannot occur while the previous plan's kernels are still ordered before it on the same stream.)"""
+    key = (index.data_ptr(), index._version, index.numel(), s, index.device.index,
+           torch.cuda.current_stream(index.device).cuda_stream)
+    hit = _PLAN_CACHE.get(key)
+    if hit is not None and hit[0]() is index:
+        return hit[1]
+    plan = sp_sort(index, s)
+    if len(_PLAN_CACHE) >= 8:
+        _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    import weakref
+    _PLAN_CACHE[key] = (weakref.ref(index), plan)
+    return plan
+
+
 def scatter_mean(src: torch.Tensor, index: torch.Tensor, dim: int = -1, out: Optional[torch.Tensor] = None,
                  dim_size: Optional[int] = None, exact: bool = True) -> torch.Tensor:
     """Drop-in for ``torch_scatter.scatter_mean`` on the reference's call pattern: float32 ``src`` of
@@ -190,7 +211,7 @@ def scatter_mean(src: torch.Tensor, index: torch.Tensor, dim: int = -1, out: Opt
         res = _ScatterMeanFn.apply(src2, index, s, exact)
         plan = None
     else:
-        plan = sp_sort(index, s)
+        plan = _cached_plan(index, s)
         res = sp_mean(src2, plan, exact=exact)
     if orig_dtype != torch.float32:
         res = res.to(orig_dtype)

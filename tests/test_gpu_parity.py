@@ -466,3 +466,18 @@ def test_pth_producer_feeds_the_reference_loader(tmp_path, small_scene):
     loaded = sd.load_points_2dfeats(str(tmp_path), "scene0001_00")
     want = lo.scale_mean_oracle(lo.lift_features_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, [sc.fmap, fm2]))
     assert torch.equal(loaded, want)
+
+
+def test_scatter_mean_plan_cache_tracks_index_version():
+    """Back-to-back scatter_mean calls with the same index object share one sort (spconvunet.py:390,392,325);
+    an in-place change of the index must invalidate it."""
+    g = torch.Generator().manual_seed(8)
+    idx = torch.randint(0, 50, (4000,), generator=g)
+    idx_d = idx.to(DEV)
+    for c in (32, 256, 3):
+        src = torch.randn(4000, c, generator=g)
+        assert torch.equal(sd.scatter_mean(src.to(DEV), idx_d, dim=0).cpu(), so.scatter_mean_oracle(src, idx, dim=0))
+    idx_d += 1
+    idx += 1
+    src = torch.randn(4000, 16, generator=g)
+    assert torch.equal(sd.scatter_mean(src.to(DEV), idx_d, dim=0).cpu(), so.scatter_mean_oracle(src, idx, dim=0))
