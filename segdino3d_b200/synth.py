@@ -120,10 +120,14 @@ def _make_cameras(g: torch.Generator, v: int):
     return c2w, w2c
 
 
-def _render_depth(xyz64: torch.Tensor, w2c64: torch.Tensor, hd: int, wd: int, sx: float, sy: float) -> torch.Tensor:
-    """z-buffer splat of the scene's own points + 3x3 min dilation; holes stay 0 (= invalid)."""
+def _render_depth(xyz64: torch.Tensor, w2c64: torch.Tensor, hd: int, wd: int, sx: float, sy: float,
+                  device=None) -> torch.Tensor:
+    """z-buffer splat of the scene's own points + 3x3 min dilation; holes stay 0 (= invalid).
+    ``device``: render there (bench only, large scenes); the result is returned on that device."""
     v = w2c64.shape[0]
-    out = torch.zeros(v, hd, wd, dtype=torch.float32)
+    if device is not None:
+        xyz64, w2c64 = xyz64.to(device), w2c64.to(device)
+    out = torch.zeros(v, hd, wd, dtype=torch.float32, device=xyz64.device)
     big = 1e9
     for i in range(v):
         r, t = w2c64[i, :, :3], w2c64[i, :, 3]
@@ -136,7 +140,7 @@ def _render_depth(xyz64: torch.Tensor, w2c64: torch.Tensor, hd: int, wd: int, sx
         wi = torch.floor(w + 0.5)
         ok &= (ui >= 0) & (ui < wd) & (wi >= 0) & (wi < hd)
         lin = (wi[ok] * wd + ui[ok]).long()
-        zb = torch.full((hd * wd,), big, dtype=torch.float64)
+        zb = torch.full((hd * wd,), big, dtype=torch.float64, device=xyz64.device)
         zb.scatter_reduce_(0, lin, z[ok], reduce="amin")
         zb = zb.view(1, 1, hd, wd)
         zb = -torch.nn.functional.max_pool2d(-zb, 3, stride=1, padding=1)
@@ -188,7 +192,8 @@ def make_scene(n_points: int = 100_000, n_views: int = 40, hd: int = 480, wd: in
     k = torch.tensor([FX * sx, FY * sy, (CX + 0.5) * sx - 0.5, (CY + 0.5) * sy - 0.5], dtype=torch.float64)
     K = k.float().repeat(n_views, 1).contiguous()
     w2c = w2c64.float().contiguous()
-    depth = _render_depth(xyz64, w2c64, hd, wd, sx, sy)
+    depth = _render_depth(xyz64, w2c64, hd, wd, sx, sy,
+                          device=fmap_device if (fmap_device is not None and n_points * n_views > 50_000_000) else None)
     hf, wf = hd // stride, wd // stride
     if fmap_device is not None and torch.device(fmap_device).type == "cuda":
         gd = torch.Generator(device=fmap_device)

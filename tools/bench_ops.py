@@ -54,7 +54,15 @@ for k, s, n in [(600, 500, 100_000), (600, 5000, 1_000_000)]:
     def ref(i):
         mp = m[:, sp] > 0.35
         return mp, mp.sum(1)
-    for name, fn in (("sd3d", lambda i: sd.expand_superpoint_masks(m, sp, 0.35)), ("torch_index+gt+sum", ref)):
+    from segdino3d_b200 import _lib
+    from segdino3d_b200.ops import _ptr, _stream
+    lib = _lib.load()
+    out = torch.empty(k, n, dtype=torch.uint8, device=dev)
+    pn = torch.empty(k, dtype=torch.int32, device=dev)
+    def raw(i):  # the C-ABI call alone (no allocation): what the kernel itself costs
+        lib.sd3d_sp_expand_mask(_ptr(m), _ptr(sp), k, s, n, 0.35, _ptr(out), _ptr(pn), _stream())
+    for name, fn in (("sd3d", lambda i: sd.expand_superpoint_masks(m, sp, 0.35)), ("sd3d_abi_only", raw),
+                     ("torch_index+gt+sum", ref)):
         t = timeit(fn, 30)
         res[name] = {"us": round(t * 1e6, 1), "GBps": round(bytes_alg / t / 1e9, 1), "frac_hbm": round(bytes_alg / t / 1e9 / PEAK, 3)}
     print(json.dumps(res), flush=True)
