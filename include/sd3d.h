@@ -110,7 +110,9 @@ int sd3d_sp_mean(const float* src, const int32_t* perm, const int32_t* seg_offse
  *   bit 1 = view-synchronous tile gather kernel instead of the point-streaming one (same results; bits 2-4
  *   tune it: 4 = register double buffer, 8 = no per-view barrier, 16 = no L1 prefetch);
  *   bit 8 (256) = run the projection kernel only, bit 9 (512) = run the gather kernel only on the masks a
- *   previous projection-only call left in the same ws (per-kernel timing, stream overlap).
+ *   previous projection-only call left in the same ws (per-kernel timing, stream overlap);
+ *   bit 10 (1024) = rows of out_feat / count are indexed by processing position i (point order[i]) instead
+ *   of by point id: chunks of the processing order are then contiguous (multi-GPU chunked exchange).
  * --------------------------------------------------------------------------------------------- */
 size_t sd3d_lift_workspace_bytes(int64_t N, int n_views, int C, int64_t max_tasks);
 int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin, int view_end,

@@ -36,6 +36,7 @@ struct LiftParams {
     int Hf, Wf, C;
     float stride, tau, z_near;
     int accumulate, finalize;
+    int by_pos;  // rows of out / count are indexed by processing position instead of point id
     const int32_t* order;
     float* out;
     int32_t* count;
@@ -306,6 +307,7 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
 
     for (int64_t i = start + warp; i < end; i += kLiftWarps) {
         const int32_t pid = p.order ? p.order[i] : (int32_t)i;
+        const int64_t orow = p.by_pos ? i : (int64_t)pid;  // output row
         const float px = __ldg(p.xyz + 3 * (int64_t)pid), py = __ldg(p.xyz + 3 * (int64_t)pid + 1),
                     pz = __ldg(p.xyz + 3 * (int64_t)pid + 2);
         const uint32_t* __restrict__ mw = masks + (int64_t)pid * nchunks;
@@ -316,11 +318,11 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
         for (int k = 0; k < NV; ++k) acc[k] = f4_zero();
         int cnt = n_total;
         if (p.accumulate) {
-            cnt += p.count[pid];
+            cnt += p.count[orow];
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
                 const int c = (k * 32 + lane) * 4;
-                if (c < p.C) acc[k] = *reinterpret_cast<const float4*>(p.out + (int64_t)pid * p.C + c);
+                if (c < p.C) acc[k] = *reinterpret_cast<const float4*>(p.out + orow * p.C + c);
             }
         }
         for (int r0 = 0; r0 < n_total; r0 += 32) {
@@ -379,11 +381,11 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
             const int c = (k * 32 + lane) * 4;
             if (c < p.C) {
                 const float4 o = p.finalize ? f4_div(acc[k], denom) : acc[k];
-                st_cs_f4(p.out + (int64_t)pid * p.C + c, o);
+                st_cs_f4(p.out + orow * p.C + c, o);
                 sp_acc[k] = f4_add(sp_acc[k], o);
             }
         }
-        if (lane == 0) p.count[pid] = cnt;
+        if (lane == 0) p.count[orow] = cnt;
     }
     if (p.pool && seg < p.S) {  // uniform per CTA
 #pragma unroll
@@ -715,7 +717,7 @@ static int dispatch_gather(const LiftParams& p, const uint32_t* masks, int nchun
                            cudaStream_t stream) {
     const int nv = (p.C + 127) / 128;
     const bool fast = (variant & 1) != 0;
-    const bool tk = (variant & 2) != 0 && nchunks <= kMaxChunks;
+    const bool tk = (variant & 2) != 0 && nchunks <= kMaxChunks && !p.by_pos;
     const bool db = (variant & 4) != 0;
     const int tf = (variant >> 3) & 15;  // experiment bits: 8 = tile: no per-view barrier, 16 = tile: no L1 prefetch,
                                          // 32 / 64 = streaming kernel compiled for 5 / 3 CTAs per SM
@@ -802,7 +804,7 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
     p.xyz = xyz; p.N = N; p.K4 = K4; p.w2c = w2c; p.v_begin = view_begin; p.v_end = view_end;
     p.depth = depth; p.depth_u16 = depth_dtype == SD3D_U16; p.Hd = Hd; p.Wd = Wd;
     p.fmap = fmap; p.Hf = Hf; p.Wf = Wf; p.C = C; p.stride = stride; p.tau = tau; p.z_near = z_near;
-    p.accumulate = accumulate; p.finalize = finalize; p.order = order; p.out = out_feat; p.count = count;
+    p.accumulate = accumulate; p.finalize = finalize; p.by_pos = (variant & 1024) ? 1 : 0; p.order = order; p.out = out_feat; p.count = count;
     p.pix_idx = pix_idx; p.vis = vis; p.pool = pool ? 1 : 0; p.seg_offsets = seg_offsets;
     p.task_offsets = task_offsets; p.task_seg = task_seg; p.S = (int32_t)S; p.run = run;
     p.partials = reinterpret_cast<float*>(ws);

@@ -131,6 +131,117 @@ def lift_view_sharded(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: torch
     return out
 
 
+def lift_view_sharded_overlapped(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: torch.Tensor,
+                                 depth_local: torch.Tensor, fmap_local: torch.Tensor, sp_ids: torch.Tensor,
+                                 n_superpoints: int, *, stride: Optional[float] = None, tau: float = 0.05,
+                                 z_near: float = 0.1, n_chunks: int = 4, variant: int = 0, group=None):
+    """View-sharded lifting with the NVLink exchange OVERLAPPED with the gather (CUDA + NCCL only).
+
+    The partial sums are written in *processing-position* order, laid out chunk-major so that chunk k is one
+    contiguous block holding, for every rank r, the k-th slice of r's position shard:
+
+        buffer row j = k*(R*B) + r*B + b   <->   position r*(n_chunks*B) + k*B + b   <->   point order[position]
+
+    Chunk k is gathered by one launch of the gather kernel (same kernel, `order`/`out` pointers offset, rows
+    indexed by position); as soon as it is done a reduce_scatter of that block runs on a second stream while
+    chunk k+1 is being gathered. Rank r ends up with the reduced rows of the CONTIGUOUS position shard
+    [r*n_chunks*B, (r+1)*n_chunks*B), finalises them, pools the superpoint pieces inside its shard and an
+    all-reduce of the small [S,C] sums (+ sizes) finishes the pooling.
+
+    Returns a dict: ``feat_shard`` (rows = positions ``rows[0]..rows[1]`` of ``order``), ``order`` (int32 [N]:
+    position -> point id), ``count`` (int32 [N] by POINT id), ``sp_feat`` [S,C] (same on every rank)."""
+    from . import _lib, ops as _ops
+    from .ops import _ptr, _stream, _DEPTH_CODE, _FMAP_CODE, SuperpointPlan
+    lib = _lib.load()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    dev = xyz.device
+    n, c = xyz.shape[0], fmap_local.shape[3]
+    v = K_local.shape[0]
+    hd, wd = depth_local.shape[1], depth_local.shape[2]
+    hf, wf = fmap_local.shape[1], fmap_local.shape[2]
+    stride = float(wd / wf if stride is None else stride)
+    xyz, K_local, w2c_local, depth_local, fmap_local = (t.contiguous() for t in (xyz, K_local, w2c_local, depth_local, fmap_local))
+    s = int(n_superpoints)
+    plan = _ops.sp_sort(sp_ids, s, xyz=xyz)
+    blk = (n + world * n_chunks - 1) // (world * n_chunks)
+    blk = (blk + 31) // 32 * 32                       # B: rows per (chunk, rank) block
+    shard_rows = n_chunks * blk                       # positions owned by one rank
+    n_pad = world * shard_rows
+    # j -> position, and the padded processing order in j-order
+    pos_of_j = torch.arange(n_pad, device=dev).view(world, n_chunks, blk).permute(1, 0, 2).reshape(-1)
+    order_pad = torch.cat([plan.order, plan.order.new_zeros(n_pad - n)]) if n_pad > n else plan.order
+    order_j = order_pad[pos_of_j].contiguous()        # padding rows lift point order[0] again and are discarded
+    sum_j = torch.empty(n_pad, c, dtype=torch.float32, device=dev)
+    cnt_j = torch.empty(n_pad, dtype=torch.int32, device=dev)
+    shard = torch.empty(shard_rows, c, dtype=torch.float32, device=dev)
+    ws_bytes = int(lib.sd3d_lift_workspace_bytes(n, v, c, 0))
+    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+
+    def call(stage_bits, n_sub, order_t, out_t, cnt_t):
+        _lib.check(lib.sd3d_lift(_ptr(xyz), n_sub, _ptr(K_local), _ptr(w2c_local), v, 0, v, _ptr(depth_local),
+                                 _DEPTH_CODE[depth_local.dtype], hd, wd, _ptr(fmap_local), _FMAP_CODE[fmap_local.dtype],
+                                 hf, wf, c, stride, float(tau), float(z_near), 0, 0, _ptr(order_t), _ptr(out_t),
+                                 _ptr(cnt_t), None, None, None, 0, None, None, 0, _ops.DEFAULT_RUN, _ptr(ws), ws_bytes, 0,
+                                 int(variant) | stage_bits, _stream()), "sd3d_lift")
+
+    compute = torch.cuda.current_stream(dev)
+    comm = _comm_stream(dev)
+    with torch.cuda.device(dev):
+        call(256, n, None, sum_j, cnt_j)              # projection of every point against the local views
+        works = []
+        chunk_rows = world * blk
+        for k in range(n_chunks):
+            lo = k * chunk_rows
+            call(512 | 1024, chunk_rows, order_j[lo:], sum_j[lo:], cnt_j[lo:])
+            if world > 1:
+                ev = torch.cuda.Event()
+                ev.record(compute)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ev)
+                    works.append(dist.reduce_scatter_tensor(shard[k * blk:(k + 1) * blk], sum_j[lo:lo + chunk_rows],
+                                                            op=dist.ReduceOp.SUM, group=group, async_op=True))
+            else:
+                shard[k * blk:(k + 1) * blk].copy_(sum_j[lo:lo + chunk_rows])
+        if world > 1:
+            with torch.cuda.stream(comm):
+                works.append(dist.all_reduce(cnt_j, op=dist.ReduceOp.SUM, group=group, async_op=True))
+            for w in works:
+                w.wait()                               # the compute stream waits for the exchange
+        # this rank's contiguous position shard
+        b = rank * shard_rows
+        e = min(b + shard_rows, n)
+        valid = max(e - b, 0)
+        cnt_shard = cnt_j.view(n_chunks, world, blk)[:, rank, :].reshape(-1)[:valid].contiguous()
+        feat_shard = _ops.lift_finalize(shard[:valid], cnt_shard) if valid > 0 else shard[:0]
+        # superpoint pieces inside the shard: clip the global segment offsets to [b, e)
+        off = plan.seg_offsets[: s + 1].clamp(min=b, max=max(e, b)) - b
+        off_local = torch.cat([off, off.new_full((1,), valid)]).to(torch.int32).contiguous()
+        ident = torch.arange(valid, dtype=torch.int32, device=dev)
+        local_plan = SuperpointPlan(ident, ident, off_local, off_local, off_local, valid, s, _ops.DEFAULT_RUN, 0)
+        sizes = (off_local[1: s + 1] - off_local[:s]).to(torch.float32)
+        sp_sum = _ops.sp_mean(feat_shard.contiguous(), local_plan, exact=True) * sizes[:, None]
+        if world > 1:
+            dist.all_reduce(sp_sum, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(sizes, op=dist.ReduceOp.SUM, group=group)
+        sp_feat = sp_sum / sizes.clamp(min=1)[:, None]
+        # global counts by point id
+        cnt_pos = cnt_j.view(n_chunks, world, blk).permute(1, 0, 2).reshape(-1)[:n]
+        count = torch.empty(n, dtype=torch.int32, device=dev)
+        count[plan.order.long()] = cnt_pos
+    return {"feat_shard": feat_shard, "rows": (b, e), "order": plan.order, "count": count, "sp_feat": sp_feat}
+
+
+_COMM_STREAMS = {}
+
+
+def _comm_stream(dev: torch.device) -> torch.cuda.Stream:
+    st = _COMM_STREAMS.get(dev.index)
+    if st is None:
+        st = _COMM_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return st
+
+
 # ------------------------------------------------------------------------------------------------------
 # bench leg (bench.py --mode viewshard): one large scene, strong scaling over ranks
 # ------------------------------------------------------------------------------------------------------
@@ -151,6 +262,9 @@ def bench_viewshard(args, rank: int, world: int, dev: torch.device):
     ops = cuda_ops(variant=args.variant)
 
     def step():
+        if args.exchange == "overlap":
+            return lift_view_sharded_overlapped(d["xyz"], K_l, w2c_l, depth_l, fmap_l, d["sp_ids"], sc.n_superpoints,
+                                                stride=sc.stride, n_chunks=args.chunks, variant=args.variant)
         return lift_view_sharded(d["xyz"], K_l, w2c_l, depth_l, fmap_l, d["sp_ids"], sc.n_superpoints,
                                  stride=sc.stride, exchange=args.exchange, ops=ops)
 

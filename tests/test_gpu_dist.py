@@ -33,10 +33,20 @@ def _worker(rank, world, port, exchange, out_dir):
         from segdino3d_b200.synth import make_scene
         sc = make_scene(n_points=20_001, n_views=23, hd=120, wd=160, stride=8, channels=256, seed=41, sp_target=100)
         vb, ve = shard_range(23, world, rank)
-        r = lift_view_sharded(sc.xyz.to(dev), sc.K[vb:ve].contiguous().to(dev), sc.w2c[vb:ve].contiguous().to(dev),
-                              sc.depth[vb:ve].contiguous().to(dev), sc.fmap[vb:ve].contiguous().to(dev),
-                              sc.sp_ids.to(dev), sc.n_superpoints, stride=sc.stride, exchange=exchange,
-                              gather_feats=True)
+        args = (sc.xyz.to(dev), sc.K[vb:ve].contiguous().to(dev), sc.w2c[vb:ve].contiguous().to(dev),
+                sc.depth[vb:ve].contiguous().to(dev), sc.fmap[vb:ve].contiguous().to(dev), sc.sp_ids.to(dev),
+                sc.n_superpoints)
+        if exchange == "overlap":
+            from segdino3d_b200.dist import lift_view_sharded_overlapped
+            r = lift_view_sharded_overlapped(*args, stride=sc.stride, n_chunks=3)
+            # rebuild the full point-id-ordered feature matrix from the position shards of all ranks
+            full = torch.zeros(sc.xyz.shape[0], r["feat_shard"].shape[1], device=dev)
+            b, e = r["rows"]
+            full[r["order"][b:e].long()] = r["feat_shard"]
+            dist.all_reduce(full)
+            r = {"feat": full, "count": r["count"], "sp_feat": r["sp_feat"]}
+        else:
+            r = lift_view_sharded(*args, stride=sc.stride, exchange=exchange, gather_feats=True)
         torch.cuda.synchronize()
         torch.save({k: (v.cpu() if torch.is_tensor(v) else v) for k, v in r.items()}, os.path.join(out_dir, f"r{rank}.pt"))
     finally:
@@ -44,7 +54,7 @@ def _worker(rank, world, port, exchange, out_dir):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("exchange", ["allreduce", "reduce_scatter"])
+@pytest.mark.parametrize("exchange", ["allreduce", "reduce_scatter", "overlap"])
 def test_view_sharded_nccl_matches_oracle(tmp_path, exchange):
     from oracle import lift_oracle as lo
     from oracle import scatter_oracle as so
