@@ -163,21 +163,15 @@ def lift_view_sharded_overlapped(xyz: torch.Tensor, K_local: torch.Tensor, w2c_l
     stride = float(wd / wf if stride is None else stride)
     xyz, K_local, w2c_local, depth_local, fmap_local = (t.contiguous() for t in (xyz, K_local, w2c_local, depth_local, fmap_local))
     s = int(n_superpoints)
-    plan = _ops.sp_sort(sp_ids, s, xyz=xyz)
     blk = (n + world * n_chunks - 1) // (world * n_chunks)
     blk = (blk + 31) // 32 * 32                       # B: rows per (chunk, rank) block
     shard_rows = n_chunks * blk                       # positions owned by one rank
     n_pad = world * shard_rows
-    # j -> position, and the padded processing order in j-order
-    pos_of_j = torch.arange(n_pad, device=dev).view(world, n_chunks, blk).permute(1, 0, 2).reshape(-1)
-    order_pad = torch.cat([plan.order, plan.order.new_zeros(n_pad - n)]) if n_pad > n else plan.order
-    order_j = order_pad[pos_of_j].contiguous()        # padding rows lift point order[0] again and are discarded
     sum_j = torch.empty(n_pad, c, dtype=torch.float32, device=dev)
     cnt_j = torch.empty(n_pad, dtype=torch.int32, device=dev)
     shard = torch.empty(shard_rows, c, dtype=torch.float32, device=dev)
     ws_bytes = int(lib.sd3d_lift_workspace_bytes(n, v, c, 0))
     ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-
     def call(stage_bits, n_sub, order_t, out_t, cnt_t):
         _lib.check(lib.sd3d_lift(_ptr(xyz), n_sub, _ptr(K_local), _ptr(w2c_local), v, 0, v, _ptr(depth_local),
                                  _DEPTH_CODE[depth_local.dtype], hd, wd, _ptr(fmap_local), _FMAP_CODE[fmap_local.dtype],
@@ -188,7 +182,32 @@ def lift_view_sharded_overlapped(xyz: torch.Tensor, K_local: torch.Tensor, w2c_l
     compute = torch.cuda.current_stream(dev)
     comm = _comm_stream(dev)
     with torch.cuda.device(dev):
-        call(256, n, None, sum_j, cnt_j)              # projection of every point against the local views
+        # projection of every point against the local views on the side stream, concurrently with the plan
+        fork, join = torch.cuda.Event(), torch.cuda.Event()
+        fork.record(compute)
+        with torch.cuda.stream(comm):
+            comm.wait_event(fork)
+            call(256, n, None, sum_j, cnt_j)
+            join.record(comm)
+        plan = _ops.sp_sort(sp_ids, s, xyz=xyz)
+        # "positions" follow the run table: superpoints along the world Morton curve (L2 locality of the gather),
+        # refined order inside each superpoint; superpoints stay contiguous
+        seg_first_task = plan.task_offsets[: s + 1].long()
+        seg_order = torch.argsort(seg_first_task)                      # segments (incl. the invalid-id one) by task rank
+        old_off = plan.seg_offsets.long()
+        sizes_all = (old_off[1: s + 2] - old_off[: s + 1])
+        new_sizes = sizes_all[seg_order]
+        new_off_sorted = torch.cumsum(new_sizes, 0) - new_sizes        # start of every segment in the new sequence
+        seg_of_pos = torch.repeat_interleave(torch.arange(s + 1, device=dev), new_sizes, output_size=n)
+        old_pos = old_off[seg_order][seg_of_pos] + (torch.arange(n, device=dev) - new_off_sorted[seg_of_pos])
+        order_t = plan.order[old_pos]                                  # int32 [N]: position -> point id
+        seg_off_t = torch.empty(s + 1, dtype=torch.long, device=dev)   # start of superpoint id s in the new sequence
+        seg_off_t[seg_order] = new_off_sorted
+        seg_size_t = sizes_all
+        pos_of_j = _pos_of_j(n_pad, world, n_chunks, blk, dev)
+        order_pad = torch.cat([order_t, order_t.new_zeros(n_pad - n)]) if n_pad > n else order_t
+        order_j = order_pad[pos_of_j].contiguous()    # padding rows lift point order[0] again and are discarded
+        compute.wait_event(join)
         works = []
         chunk_rows = world * blk
         for k in range(n_chunks):
@@ -214,12 +233,19 @@ def lift_view_sharded_overlapped(xyz: torch.Tensor, K_local: torch.Tensor, w2c_l
         valid = max(e - b, 0)
         cnt_shard = cnt_j.view(n_chunks, world, blk)[:, rank, :].reshape(-1)[:valid].contiguous()
         feat_shard = _ops.lift_finalize(shard[:valid], cnt_shard) if valid > 0 else shard[:0]
-        # superpoint pieces inside the shard: clip the global segment offsets to [b, e)
-        off = plan.seg_offsets[: s + 1].clamp(min=b, max=max(e, b)) - b
-        off_local = torch.cat([off, off.new_full((1,), valid)]).to(torch.int32).contiguous()
-        ident = torch.arange(valid, dtype=torch.int32, device=dev)
-        local_plan = SuperpointPlan(ident, ident, off_local, off_local, off_local, valid, s, _ops.DEFAULT_RUN, 0)
-        sizes = (off_local[1: s + 1] - off_local[:s]).to(torch.float32)
+        # superpoint pieces inside the shard: clip every superpoint's [start, end) to [b, e). The pieces are not
+        # in id order, so the pooling kernel gets them through an explicit (piece start, piece end) table:
+        # perm = shard rows listed superpoint by superpoint, offsets = running piece sizes
+        st = seg_off_t.clamp(min=b, max=max(e, b)) - b                         # [S+1] incl. the invalid-id segment
+        en = (seg_off_t + seg_size_t).clamp(min=b, max=max(e, b)) - b
+        piece = en - st                                                        # sums to `valid` exactly
+        off_local = torch.zeros(s + 2, dtype=torch.long, device=dev)
+        off_local[1:] = torch.cumsum(piece, 0)
+        seg_of_row = torch.repeat_interleave(torch.arange(s + 1, device=dev), piece, output_size=int(valid))
+        rows_by_seg = (st[seg_of_row] + (torch.arange(valid, device=dev) - off_local[: s + 1][seg_of_row])).to(torch.int32)
+        off32 = off_local.to(torch.int32).contiguous()
+        local_plan = SuperpointPlan(rows_by_seg.contiguous(), rows_by_seg, off32, off32, off32, valid, s, _ops.DEFAULT_RUN, 0)
+        sizes = piece[:s].to(torch.float32)
         sp_sum = _ops.sp_mean(feat_shard.contiguous(), local_plan, exact=True) * sizes[:, None]
         if world > 1:
             dist.all_reduce(sp_sum, op=dist.ReduceOp.SUM, group=group)
@@ -228,11 +254,24 @@ def lift_view_sharded_overlapped(xyz: torch.Tensor, K_local: torch.Tensor, w2c_l
         # global counts by point id
         cnt_pos = cnt_j.view(n_chunks, world, blk).permute(1, 0, 2).reshape(-1)[:n]
         count = torch.empty(n, dtype=torch.int32, device=dev)
-        count[plan.order.long()] = cnt_pos
-    return {"feat_shard": feat_shard, "rows": (b, e), "order": plan.order, "count": count, "sp_feat": sp_feat}
+        count[order_t.long()] = cnt_pos
+    return {"feat_shard": feat_shard, "rows": (b, e), "order": order_t, "count": count, "sp_feat": sp_feat}
 
 
 _COMM_STREAMS = {}
+_POS_CACHE = {}
+
+
+def _pos_of_j(n_pad: int, world: int, n_chunks: int, blk: int, dev: torch.device) -> torch.Tensor:
+    """buffer row j -> position (static for a given geometry; cached)."""
+    key = (n_pad, world, n_chunks, blk, dev.index)
+    t = _POS_CACHE.get(key)
+    if t is None:
+        if len(_POS_CACHE) > 8:
+            _POS_CACHE.clear()
+        t = torch.arange(n_pad, device=dev).view(world, n_chunks, blk).permute(1, 0, 2).reshape(-1).contiguous()
+        _POS_CACHE[key] = t
+    return t
 
 
 def _comm_stream(dev: torch.device) -> torch.cuda.Stream:
