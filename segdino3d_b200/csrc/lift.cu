@@ -52,25 +52,44 @@ struct LiftParams {
     float* partials;
 };
 
+// One 128-bit load per lane per tap row: 4 fp32 channels, or 8 fp16 / bf16 channels (= two float4 registers).
+// chan_of(k, lane) = first channel held by float4 register k of this lane.
 template <typename FT>
-__device__ __forceinline__ float4 load_tap(const FT* p);
+struct Tap;
 template <>
-__device__ __forceinline__ float4 load_tap<float>(const float* p) {
-    return __ldg(reinterpret_cast<const float4*>(p));
-}
+struct Tap<float> {
+    static constexpr int kElems = 4, kRegs = 1;
+    __device__ __forceinline__ static void load(float4* dst, const float* p) {
+        dst[0] = __ldg(reinterpret_cast<const float4*>(p));
+    }
+};
 template <>
-__device__ __forceinline__ float4 load_tap<__half>(const __half* p) {
-    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
-    const __half2 a = *reinterpret_cast<const __half2*>(&raw.x);
-    const __half2 b = *reinterpret_cast<const __half2*>(&raw.y);
-    const float2 fa = __half22float2(a), fb = __half22float2(b);
-    return make_float4(fa.x, fa.y, fb.x, fb.y);
-}
+struct Tap<__half> {
+    static constexpr int kElems = 8, kRegs = 2;
+    __device__ __forceinline__ static void load(float4* dst, const __half* p) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&raw.z));
+        const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&raw.w));
+        dst[0] = make_float4(a.x, a.y, b.x, b.y);
+        dst[1] = make_float4(c.x, c.y, d.x, d.y);
+    }
+};
 template <>
-__device__ __forceinline__ float4 load_tap<__nv_bfloat16>(const __nv_bfloat16* p) {
-    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(p));
-    return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
-                       __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+struct Tap<__nv_bfloat16> {
+    static constexpr int kElems = 8, kRegs = 2;
+    __device__ __forceinline__ static void load(float4* dst, const __nv_bfloat16* p) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+        dst[0] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                             __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+        dst[1] = make_float4(__uint_as_float(raw.z << 16), __uint_as_float(raw.z & 0xffff0000u),
+                             __uint_as_float(raw.w << 16), __uint_as_float(raw.w & 0xffff0000u));
+    }
+};
+template <typename FT>
+__device__ __forceinline__ int chan_of(int k, int lane) {
+    return ((k / Tap<FT>::kRegs) * 32 + lane) * Tap<FT>::kElems + (k % Tap<FT>::kRegs) * 4;
 }
 
 // f = ((w00*t00 + w01*t01) + w10*t10) + w11*t11 ; acc = acc + f      (Appendix A, unfused)
@@ -136,26 +155,30 @@ __device__ __forceinline__ void sample_issue(Sample<NV>& s, const SampleScalars&
     s.w10 = __shfl_sync(kFull, mine.w10, src_lane);
     s.w11 = __shfl_sync(kFull, mine.w11, src_lane);
     const int flags = (vf >> 24) & 0xF;
-    const FT* __restrict__ p00 = fmap + (int64_t)(vf & 0xFFFFFF) * view_elems + o00 + lane * 4;
+    constexpr int kE = Tap<FT>::kElems, kR = Tap<FT>::kRegs;
+    static_assert(NV % kR == 0, "register vectors per tap must be a multiple of the registers one load fills");
+    const FT* __restrict__ p00 = fmap + (int64_t)(vf & 0xFFFFFF) * view_elems + o00 + lane * kE;
     const FT* __restrict__ p10 = p00 + row_elems;
     if (flags == 0xF) {  // interior sample (the common case): unpredicated-on-validity loads
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            if ((k * 32 + lane) * 4 < C) {
-                s.t00[k] = load_tap<FT>(p00 + k * 128);
-                s.t01[k] = load_tap<FT>(p00 + C + k * 128);
-                s.t10[k] = load_tap<FT>(p10 + k * 128);
-                s.t11[k] = load_tap<FT>(p10 + C + k * 128);
+        for (int l = 0; l < NV / kR; ++l) {
+            if ((l * 32 + lane) * kE < C) {
+                Tap<FT>::load(&s.t00[l * kR], p00 + l * 32 * kE);
+                Tap<FT>::load(&s.t01[l * kR], p00 + C + l * 32 * kE);
+                Tap<FT>::load(&s.t10[l * kR], p10 + l * 32 * kE);
+                Tap<FT>::load(&s.t11[l * kR], p10 + C + l * 32 * kE);
             }
         }
     } else {  // border sample: taps outside the map read as zero (Appendix A `tap(y,x)`)
 #pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            const bool cok = (k * 32 + lane) * 4 < C;
-            s.t00[k] = (cok && (flags & 1)) ? load_tap<FT>(p00 + k * 128) : f4_zero();
-            s.t01[k] = (cok && (flags & 2)) ? load_tap<FT>(p00 + C + k * 128) : f4_zero();
-            s.t10[k] = (cok && (flags & 4)) ? load_tap<FT>(p10 + k * 128) : f4_zero();
-            s.t11[k] = (cok && (flags & 8)) ? load_tap<FT>(p10 + C + k * 128) : f4_zero();
+        for (int l = 0; l < NV / kR; ++l) {
+            const bool cok = (l * 32 + lane) * kE < C;
+#pragma unroll
+            for (int r = 0; r < kR; ++r) s.t00[l * kR + r] = s.t01[l * kR + r] = s.t10[l * kR + r] = s.t11[l * kR + r] = f4_zero();
+            if (cok && (flags & 1)) Tap<FT>::load(&s.t00[l * kR], p00 + l * 32 * kE);
+            if (cok && (flags & 2)) Tap<FT>::load(&s.t01[l * kR], p00 + C + l * 32 * kE);
+            if (cok && (flags & 4)) Tap<FT>::load(&s.t10[l * kR], p10 + l * 32 * kE);
+            if (cok && (flags & 8)) Tap<FT>::load(&s.t11[l * kR], p10 + C + l * 32 * kE);
         }
     }
 }
@@ -321,7 +344,7 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
             cnt += p.count[orow];
 #pragma unroll
             for (int k = 0; k < NV; ++k) {
-                const int c = (k * 32 + lane) * 4;
+                const int c = chan_of<FT>(k, lane);
                 if (c < p.C) acc[k] = *reinterpret_cast<const float4*>(p.out + orow * p.C + c);
             }
         }
@@ -378,7 +401,7 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
         const float denom = (float)max(cnt, 1);
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
-            const int c = (k * 32 + lane) * 4;
+            const int c = chan_of<FT>(k, lane);
             if (c < p.C) {
                 const float4 o = p.finalize ? f4_div(acc[k], denom) : acc[k];
                 st_cs_f4(p.out + orow * p.C + c, o);
@@ -397,7 +420,7 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
                 float4 t = s_red[0][k * 32 + lane];
 #pragma unroll
                 for (int w = 1; w < kLiftWarps; ++w) t = f4_add(t, s_red[w][k * 32 + lane]);
-                const int c = (k * 32 + lane) * 4;
+                const int c = chan_of<FT>(k, lane);
                 if (c < p.C) *reinterpret_cast<float4*>(p.partials + task * (int64_t)p.C + c) = t;
             }
         }
@@ -493,7 +516,7 @@ __global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePt
                 if (pj >= 0) {
 #pragma unroll
                     for (int k = 0; k < NV; ++k) {
-                        const int c = (k * 32 + lane) * 4;
+                        const int c = chan_of<FT>(k, lane);
                         if (c < p.C) acc[j][k] = *reinterpret_cast<const float4*>(p.out + (int64_t)pj * p.C + c);
                     }
                 }
@@ -590,7 +613,7 @@ __global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePt
                 const float denom = (float)max(cj, 1);
 #pragma unroll
                 for (int k = 0; k < NV; ++k) {
-                    const int c = (k * 32 + lane) * 4;
+                    const int c = chan_of<FT>(k, lane);
                     if (c < p.C) {
                         const float4 o = p.finalize ? f4_div(acc[j][k], denom) : acc[j][k];
                         st_cs_f4(p.out + (int64_t)pj * p.C + c, o);
@@ -612,7 +635,7 @@ __global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePt
                 float4 t = s_red[0][k * 32 + lane];
 #pragma unroll
                 for (int w = 1; w < kTileWarps; ++w) t = f4_add(t, s_red[w][k * 32 + lane]);
-                const int c = (k * 32 + lane) * 4;
+                const int c = chan_of<FT>(k, lane);
                 if (c < p.C) *reinterpret_cast<float4*>(p.partials + task * (int64_t)p.C + c) = t;
             }
         }
@@ -715,13 +738,15 @@ static void launch_gather(const LiftParams& p, const uint32_t* masks, int nchunk
 template <typename FT>
 static int dispatch_gather(const LiftParams& p, const uint32_t* masks, int nchunks, int64_t n_tasks, int variant,
                            cudaStream_t stream) {
-    const int nv = (p.C + 127) / 128;
+    // float4 registers per tap per lane: C/128 for fp32 rows, 2*ceil(C/256) for 16-bit rows (8 channels per load)
+    constexpr int kR = Tap<FT>::kRegs;
+    const int nv = kR == 1 ? (p.C + 127) / 128 : 2 * ((p.C + 255) / 256);
     const bool fast = (variant & 1) != 0;
     const bool tk = (variant & 2) != 0 && nchunks <= kMaxChunks && !p.by_pos;
     const bool db = (variant & 4) != 0;
     const int tf = (variant >> 3) & 15;  // experiment bits: 8 = tile: no per-view barrier, 16 = tile: no L1 prefetch,
                                          // 32 / 64 = streaming kernel compiled for 5 / 3 CTAs per SM
-    if (nv == 1) launch_gather<1, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);
+    if (nv == 1) launch_gather<kR, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);  // (kR == 1 only)
     else if (nv == 2) launch_gather<2, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);
     else if (nv <= 4) launch_gather<4, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);
     else if (nv <= 8) launch_gather<8, FT>(p, masks, nchunks, n_tasks, fast, tk, db, tf, stream);
@@ -760,6 +785,10 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
     }
     if (C % 4 != 0 || C > 1024) {
         set_error("sd3d_lift: C=%d must be a multiple of 4 and <= 1024", C);
+        return SD3D_ERR_UNSUPPORTED;
+    }
+    if (fmap_dtype != SD3D_F32 && C % 8 != 0) {
+        set_error("sd3d_lift: C=%d must be a multiple of 8 for 16-bit feature maps", C);
         return SD3D_ERR_UNSUPPORTED;
     }
     if (depth_dtype != SD3D_F32 && depth_dtype != SD3D_U16) {

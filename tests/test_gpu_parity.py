@@ -239,11 +239,17 @@ def test_lift_fma_variant_within_tolerance():
     assert rel_row_err(r["feat"], lo.lift_finalize_oracle(a, c), floor=1.0) <= 1e-5
 
 
+@pytest.mark.parametrize("channels", [64, 256, 512, 1024])
 @pytest.mark.parametrize("fmap_dtype", [torch.float16, torch.bfloat16])
-def test_lift_16bit_maps(fmap_dtype):
-    sc = make_scene(n_points=4000, n_views=9, hd=60, wd=80, stride=4, channels=256, seed=6, sp_target=30,
+def test_lift_16bit_maps(fmap_dtype, channels):
+    """16-bit maps are read with one 128-bit load of 8 channels per lane and tap; fp32 accumulation, bit-exact."""
+    sc = make_scene(n_points=4000, n_views=9, hd=60, wd=80, stride=4, channels=channels, seed=6, sp_target=30,
                     fmap_dtype=fmap_dtype)
     _check_lift(sc)
+    _check_lift(sc, variant=2)
+    d = sc.to(DEV)
+    with pytest.raises(sd.Sd3dError):  # 16-bit rows need C % 8 == 0
+        sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap[..., :12].contiguous(), sc.stride)
 
 
 def test_lift_u16_depth_and_many_views():
