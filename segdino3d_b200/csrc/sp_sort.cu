@@ -13,9 +13,9 @@
 //   radix pass = hist (per-block digit histogram, smem int atomics)
 //              -> scan (ONE CTA, whole bin-major [bins][blocks] matrix staged in shared memory)
 //              -> scatter (per-warp contiguous sub-chunks; __match_any_sync ranks keep equal keys in input
-//                 order; the last pass also emits a 9-bit Morton cell key per sorted point)
+//                 order; the last pass also emits a 27-bit Morton cell key per sorted point)
 //   one pass for S < 1024, ceil(log2(S+1)/10) passes otherwise (+ a boundary-search kernel).
-//   refine = per-superpoint stable counting sort by the cell key (one CTA per superpoint, 512 bins)
+//   refine = per-superpoint stable LSD counting sort by the 27-bit cell key (one CTA per superpoint, <= 3 x 512 bins)
 //   tasks  = superpoints ranked along the world Morton curve, ceil(n_s/run) runs each (ONE CTA).
 // Keys outside [0,S) are mapped to the extra key S ("trash"), which sorts last.
 #include <cooperative_groups.h>
@@ -74,12 +74,14 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {
 __device__ __forceinline__ uint32_t morton30(uint32_t x, uint32_t y, uint32_t z) {
     return spread10(x) | (spread10(y) << 1) | (spread10(z) << 2);
 }
-// position of a point inside its (8 cells)^3 block of the world grid, as a 9-bit Morton code. Points of one
-// superpoint that fall into the same block are ordered along the curve; a superpoint straddling a block
-// border is ordered piecewise -- good enough for cache locality, and it needs no bounding boxes.
-__device__ __forceinline__ uint32_t cell_key9(float x, float y, float z, float inv_cell) {
-    const int cx = (int)floorf(x * inv_cell) & 7, cy = (int)floorf(y * inv_cell) & 7, cz = (int)floorf(z * inv_cell) & 7;
-    return morton30(cx, cy, cz) & 0x1FFu;
+// position of a point inside its (512 cells)^3 block of the world grid as a 27-bit Morton code (9 bits per
+// axis; 41 m blocks at the default 8 cm cell -- larger than any indoor scene). Points of one superpoint are
+// ordered along the curve; no bounding boxes needed. Digit 0 (low 9 bits) orders points inside a (8 cells)^3
+// sub-block, digits 1 and 2 order the sub-blocks; a superpoint only pays for the digits it actually spans.
+__device__ __forceinline__ uint32_t cell_key27(float x, float y, float z, float inv_cell) {
+    const int cx = (int)floorf(x * inv_cell) & 511, cy = (int)floorf(y * inv_cell) & 511,
+              cz = (int)floorf(z * inv_cell) & 511;
+    return morton30(cx, cy, cz) & 0x7FFFFFFu;
 }
 
 template <bool FIRST>
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(kSortThreads)
                          const int32_t* __restrict__ vals_in, int64_t N, int32_t S, int shift, int bits,
                          int items_per_block, int nb, const int32_t* __restrict__ base, int32_t* __restrict__ keys_out,
                          int32_t* __restrict__ vals_out, const float* __restrict__ xyz, float inv_cell,
-                         uint16_t* __restrict__ cell_out) {
+                         uint32_t* __restrict__ cell_out) {
     extern __shared__ int32_t s_cnt[];  // [kSortWarps][bins]
     const int bins = 1 << bits;
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(kSortThreads)
             if (cell_out != nullptr) {
                 const float x = __ldg(xyz + 3 * (int64_t)val), y = __ldg(xyz + 3 * (int64_t)val + 1),
                             z = __ldg(xyz + 3 * (int64_t)val + 2);
-                cell_out[dst] = (uint16_t)cell_key9(x, y, z, inv_cell);
+                cell_out[dst] = cell_key27(x, y, z, inv_cell);
             }
         }
     }
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(kSortThreads)
                             const int32_t* __restrict__ vals_in, int64_t N, int32_t S, int shift, int bits,
                             int items_per_block, int nb, int32_t* __restrict__ hist, int32_t* __restrict__ keys_out,
                             int32_t* __restrict__ vals_out, const float* __restrict__ xyz, float inv_cell,
-                            uint16_t* __restrict__ cell_out, int32_t* __restrict__ seg_offsets) {
+                            uint32_t* __restrict__ cell_out, int32_t* __restrict__ seg_offsets) {
     extern __shared__ int32_t s_dyn[];
     __shared__ int32_t s_rowbase[1 << kMaxDigitBits];
     __shared__ int32_t s_warp[kSortWarps];
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kSortThreads)
             if (cell_out != nullptr) {
                 const float x = __ldg(xyz + 3 * (int64_t)val), y = __ldg(xyz + 3 * (int64_t)val + 1),
                             z = __ldg(xyz + 3 * (int64_t)val + 2);
-                cell_out[dst] = (uint16_t)cell_key9(x, y, z, inv_cell);
+                cell_out[dst] = cell_key27(x, y, z, inv_cell);
             }
         }
     }
@@ -378,31 +380,26 @@ __global__ void seg_bounds_kernel(const int32_t* __restrict__ sorted_keys, int64
     if (i == N) seg_offsets[S + 1] = (int32_t)N;  // end of the trash segment
 }
 
-// Spatial refinement: inside every superpoint the points are re-ordered by their 9-bit Morton cell key with a
-// stable counting sort (one CTA per superpoint; same three phases as radix_scatter_kernel), so that the points
-// one CTA lifts together project to neighbouring pixels. `order` is a permutation of `perm` inside each
-// segment; lifting results do not depend on it (only cache behaviour does). Also emits one world-grid Morton
-// key per superpoint (`anchor`, 0.25 m cells) used to walk the superpoints in a spatially coherent order.
+// Spatial refinement: inside every superpoint the points are re-ordered by their 27-bit Morton cell key with
+// up to three stable counting-sort passes of 9 bits (LSD; one CTA per superpoint; same three phases as
+// radix_scatter_kernel; passes over digits in which the superpoint's keys do not differ are skipped), so that
+// the points one CTA lifts together project to neighbouring pixels. `order` is a permutation of `perm` inside
+// each segment; lifting results do not depend on it (only cache behaviour does).
 constexpr int kRefineBins = 512;
 
-__global__ void __launch_bounds__(kSortThreads)
-    sp_refine_kernel(const float* __restrict__ xyz, const int32_t* __restrict__ perm,
-                     const uint16_t* __restrict__ cell, const int32_t* __restrict__ seg_offsets,
-                     int32_t* __restrict__ order) {
-    __shared__ int32_t s_cnt[kSortWarps][kRefineBins];
-    __shared__ int32_t s_tot[kRefineBins];
-    __shared__ int32_t s_warp[kSortWarps];
-    const int seg = blockIdx.x;
-    const int beg = seg_offsets[seg], end = seg_offsets[seg + 1];
+// one stable counting-sort pass over [beg,end) of a segment by ((key >> shift) & 511); whole CTA
+// (no __restrict__: the second pass reads what the first one wrote -- keep these off the non-coherent load path)
+__device__ __forceinline__ void seg_sort_pass(const int32_t* vals_in, const uint32_t* keys_in, int shift, int beg,
+                                              int end, int32_t* vals_out, uint32_t* keys_out,
+                                              int32_t (*s_cnt)[kRefineBins],
+                                              int32_t* s_tot, int32_t* s_warp) {
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    if (end <= beg) return;
-    (void)xyz;
     for (int i = threadIdx.x; i < kSortWarps * kRefineBins; i += blockDim.x) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     const int n = end - beg;
     const int per_warp = ((n + kSortWarps - 1) / kSortWarps + 31) / 32 * 32;
     const int wbeg = min(beg + warp * per_warp, end), wend = min(wbeg + per_warp, end);
-    for (int i = wbeg + lane; i < wend; i += 32) atomicAdd(&s_cnt[warp][cell[i]], 1);
+    for (int i = wbeg + lane; i < wend; i += 32) atomicAdd(&s_cnt[warp][(keys_in[i] >> shift) & (kRefineBins - 1)], 1);
     __syncthreads();
     // bin totals -> exclusive scan over bins (2 bins per thread) -> running offsets per (warp, bin)
     {
@@ -441,7 +438,8 @@ __global__ void __launch_bounds__(kSortThreads)
     for (int i0 = wbeg; i0 < wend; i0 += 32) {
         const int i = i0 + lane;
         const bool active = i < wend;
-        const int digit = active ? (int)cell[i] : kRefineBins;
+        const uint32_t key = active ? keys_in[i] : 0u;
+        const int digit = active ? (int)((key >> shift) & (kRefineBins - 1)) : kRefineBins;
         const unsigned peers = __match_any_sync(kFull, digit);
         const int rank = __popc(peers & ((1u << lane) - 1u));
         int32_t dst = 0;
@@ -449,7 +447,47 @@ __global__ void __launch_bounds__(kSortThreads)
         __syncwarp();
         if (active && rank == 0) s_cnt[warp][digit] += __popc(peers);
         __syncwarp();
-        if (active) order[dst] = perm[i];
+        if (active) {
+            vals_out[dst] = vals_in[i];
+            if (keys_out != nullptr) keys_out[dst] = key;
+        }
+    }
+    __syncthreads();  // the CTA's global writes are visible to the CTA's next pass
+}
+
+__global__ void __launch_bounds__(kSortThreads)
+    sp_refine_kernel(const int32_t* perm, const uint32_t* cell, const int32_t* __restrict__ seg_offsets,
+                     int32_t* tmp_perm, uint32_t* tmp_key, int64_t N, int32_t* order) {
+    __shared__ int32_t s_cnt[kSortWarps][kRefineBins];
+    __shared__ int32_t s_tot[kRefineBins];
+    __shared__ int32_t s_warp[kSortWarps];
+    __shared__ uint32_t s_span;  // OR of (key ^ first key): which digits differ inside the superpoint
+    const int seg = blockIdx.x;
+    const int beg = seg_offsets[seg], end = seg_offsets[seg + 1];
+    if (end <= beg) return;
+    if (threadIdx.x == 0) s_span = 0u;
+    __syncthreads();
+    const uint32_t k0 = cell[beg];
+    uint32_t diff = 0u;
+    for (int i = beg + threadIdx.x; i < end; i += blockDim.x) diff |= cell[i] ^ k0;
+    diff = __reduce_or_sync(kFull, diff);
+    if (lane_id() == 0 && diff) atomicOr(&s_span, diff);
+    __syncthreads();
+    const uint32_t span = s_span;
+    const int passes = (span >> 18) ? 3 : ((span >> 9) ? 2 : 1);
+    int32_t* pa = tmp_perm;
+    uint32_t* ka = tmp_key;
+    int32_t* pb = tmp_perm + N;
+    uint32_t* kb = tmp_key + N;
+    if (passes == 1) {
+        seg_sort_pass(perm, cell, 0, beg, end, order, nullptr, s_cnt, s_tot, s_warp);
+    } else if (passes == 2) {
+        seg_sort_pass(perm, cell, 0, beg, end, pa, ka, s_cnt, s_tot, s_warp);
+        seg_sort_pass(pa, ka, 9, beg, end, order, nullptr, s_cnt, s_tot, s_warp);
+    } else {
+        seg_sort_pass(perm, cell, 0, beg, end, pa, ka, s_cnt, s_tot, s_warp);
+        seg_sort_pass(pa, ka, 9, beg, end, pb, kb, s_cnt, s_tot, s_warp);
+        seg_sort_pass(pb, kb, 18, beg, end, order, nullptr, s_cnt, s_tot, s_warp);
     }
 }
 
@@ -577,7 +615,9 @@ static size_t align_up_sz(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct SortWs {
     int32_t* hist;
     int32_t* bufs;      // 4 * N ints (ping-pong keys / values of multi-pass sorts)
-    uint16_t* cell;     // N
+    uint32_t* cell;     // N   27-bit Morton cell keys of the sorted points
+    int32_t* tmp_perm;  // 2N  ping-pong buffers of the multi-pass refinement
+    uint32_t* tmp_key;  // 2N
     uint32_t* anchor;   // S + 1
 };
 
@@ -591,7 +631,9 @@ static size_t sort_ws_layout(int64_t N, int64_t S, void* ws, SortWs* out) {
     SortWs w;
     w.hist = static_cast<int32_t*>(take((size_t)kScanCap * sizeof(int32_t)));
     w.bufs = static_cast<int32_t*>(take(4 * (size_t)(N > 0 ? N : 0) * sizeof(int32_t)));
-    w.cell = static_cast<uint16_t*>(take((size_t)(N > 0 ? N : 0) * sizeof(uint16_t)));
+    w.cell = static_cast<uint32_t*>(take((size_t)(N > 0 ? N : 0) * sizeof(uint32_t)));
+    w.tmp_perm = static_cast<int32_t*>(take(2 * (size_t)(N > 0 ? N : 0) * sizeof(int32_t)));
+    w.tmp_key = static_cast<uint32_t*>(take(2 * (size_t)(N > 0 ? N : 0) * sizeof(uint32_t)));
     w.anchor = static_cast<uint32_t*>(take((size_t)(S + 1) * sizeof(uint32_t)));
     if (out) *out = w;
     return off + 256;
@@ -629,7 +671,7 @@ static int run_sort(const int64_t* idx, const float* xyz, float inv_cell, int64_
         const bool first = (p == 0), last = (p == g.passes - 1);
         int32_t* kout = last ? (g.passes > 1 ? ((p & 1) ? keysB : keysA) : nullptr) : ((p & 1) ? keysB : keysA);
         int32_t* vout = last ? perm : ((p & 1) ? valsB : valsA);
-        uint16_t* cell_out = (last && xyz != nullptr) ? w.cell : nullptr;
+        uint32_t* cell_out = (last && xyz != nullptr) ? w.cell : nullptr;
         const size_t sm_hist = (size_t)bins * sizeof(int32_t);
         const size_t sm_scat = (size_t)bins * kSortWarps * sizeof(int32_t);
         const size_t sm_scan = (size_t)bins * g.nb * sizeof(int32_t);
@@ -783,6 +825,6 @@ extern "C" int sd3d_sp_plan(const int64_t* idx, const float* xyz, int64_t N, int
     if (rc != SD3D_OK) return rc;
     rc = run_tasks(seg_offsets, perm, xyz, S, run, task_offsets, task_seg, max_tasks, stream);
     if (rc != SD3D_OK) return rc;
-    sp_refine_kernel<<<(unsigned)(S + 1), kSortThreads, 0, stream>>>(xyz, perm, w.cell, seg_offsets, order);
+    sp_refine_kernel<<<(unsigned)(S + 1), kSortThreads, 0, stream>>>(perm, w.cell, seg_offsets, w.tmp_perm, w.tmp_key, N, order);
     return check_launch("sd3d_sp_plan");
 }

@@ -77,6 +77,12 @@ def test_sp_refine_permutes_inside_segments_only():
     step_r = (sc2.xyz[seg_r][1:] - sc2.xyz[seg_r][:-1]).norm(dim=1).mean()
     step_p = (sc2.xyz[seg_p][1:] - sc2.xyz[seg_p][:-1]).norm(dim=1).mean()
     assert float(step_r) < 0.5 * float(step_p)
+    # a superpoint spanning several metres (floor / wall sized) is ordered by the full 18-bit key (two passes)
+    seg_big = order[offs[int((offs[1:] - offs[:-1]).argmax())]: offs[int((offs[1:] - offs[:-1]).argmax()) + 1]]
+    seg_bigp = perm[offs[int((offs[1:] - offs[:-1]).argmax())]: offs[int((offs[1:] - offs[:-1]).argmax()) + 1]].long()
+    big_r = (sc.xyz[seg_big][1:] - sc.xyz[seg_big][:-1]).norm(dim=1).mean()
+    big_p = (sc.xyz[seg_bigp][1:] - sc.xyz[seg_bigp][:-1]).norm(dim=1).mean()
+    assert float(big_r) < 0.2 * float(big_p)
     t_off, t_seg = plan.task_offsets.cpu().long(), plan.task_seg.cpu().long()
     sizes = torch.cat([offs[1:] - offs[:-1], torch.tensor([30_000 - int(offs[-1])])]).long()
     n_tasks = (sizes + plan.run - 1) // plan.run
