@@ -116,13 +116,21 @@ struct Sample {
 // `w11 = ...`) and broadcast with shuffles: in-view element offset of tap (y0,x0), the four weights, and
 // which taps fall inside the map (bits 0..3 = t00,t01,t10,t11).
 struct SampleScalars {
-    int view_flags;  // view index | tap-valid bits << 24
-    int o00;         // ((y0*Wf)+x0)*C, may be negative when the tap is outside (then its bit is clear)
+    // byte address of tap (y0,x0), channel 0, of the sample's view (16-byte aligned), with the tap-valid bits
+    // (bit0..3 = t00,t01,t10,t11) packed into the 4 free low bits. The address may lie outside the map when
+    // its tap is outside (then that bit is clear and the address is never dereferenced).
+    uint32_t addr_lo, addr_hi;
     float w00, w01, w10, w11;
 };
 
-__device__ __forceinline__ SampleScalars make_scalars(int view, float u, float w, float stride, int Hf, int Wf,
-                                                      int C) {
+__device__ __forceinline__ void scalars_clear(SampleScalars& r) {
+    r.addr_lo = r.addr_hi = 0u;
+    r.w00 = r.w01 = r.w10 = r.w11 = 0.f;
+}
+
+template <typename FT>
+__device__ __forceinline__ SampleScalars make_scalars(const FT* fmap, int64_t view_elems, int view, float u, float w,
+                                                      float stride, int Hf, int Wf, int C) {
     SampleScalars r;
     const float uf = __fsub_rn(__fdiv_rn(__fadd_rn(u, 0.5f), stride), 0.5f);
     const float wf = __fsub_rn(__fdiv_rn(__fadd_rn(w, 0.5f), stride), 0.5f);
@@ -136,33 +144,36 @@ __device__ __forceinline__ SampleScalars make_scalars(int view, float u, float w
     r.w11 = __fmul_rn(ax, ay);
     const bool okx0 = (x0 >= 0) && (x0 < Wf), okx1 = (x0 + 1 >= 0) && (x0 + 1 < Wf);
     const bool oky0 = (y0 >= 0) && (y0 < Hf), oky1 = (y0 + 1 >= 0) && (y0 + 1 < Hf);
-    const int flags = (int)(oky0 && okx0) | ((int)(oky0 && okx1) << 1) | ((int)(oky1 && okx0) << 2) |
-                      ((int)(oky1 && okx1) << 3);
-    r.view_flags = view | (flags << 24);
-    r.o00 = (y0 * Wf + x0) * C;
+    const uint32_t flags = (uint32_t)(oky0 && okx0) | ((uint32_t)(oky0 && okx1) << 1) | ((uint32_t)(oky1 && okx0) << 2) |
+                           ((uint32_t)(oky1 && okx1) << 3);
+    const int64_t elem = (int64_t)view * view_elems + ((int64_t)y0 * Wf + x0) * C;
+    const uint64_t addr = (uint64_t)(reinterpret_cast<uintptr_t>(fmap) + elem * (int64_t)sizeof(FT));
+    r.addr_lo = (uint32_t)addr | flags;
+    r.addr_hi = (uint32_t)(addr >> 32);
     return r;
 }
 
-// issue the 4*NV 128-bit loads of sample `src_lane` (no use of the data here -> they stay in flight)
+// issue the 4*NV 128-bit loads of sample `src_lane` (no use of the data here -> they stay in flight).
+// cmask: bit l set = this lane's l-th 128-bit vector lies inside the C channels (hoisted out of the sample loop).
 template <int NV, typename FT>
-__device__ __forceinline__ void sample_issue(Sample<NV>& s, const SampleScalars& mine, int src_lane,
-                                             const FT* __restrict__ fmap, int64_t view_elems, int C, int row_elems,
-                                             int lane) {
-    const int vf = __shfl_sync(kFull, mine.view_flags, src_lane);
-    const int o00 = __shfl_sync(kFull, mine.o00, src_lane);
+__device__ __forceinline__ void sample_issue(Sample<NV>& s, const SampleScalars& mine, int src_lane, int C,
+                                             int row_elems, int lane, unsigned cmask) {
+    constexpr int kE = Tap<FT>::kElems, kR = Tap<FT>::kRegs;
+    static_assert(NV % kR == 0, "register vectors per tap must be a multiple of the registers one load fills");
+    const uint32_t lo = __shfl_sync(kFull, mine.addr_lo, src_lane);
+    const uint32_t hi = __shfl_sync(kFull, mine.addr_hi, src_lane);
     s.w00 = __shfl_sync(kFull, mine.w00, src_lane);
     s.w01 = __shfl_sync(kFull, mine.w01, src_lane);
     s.w10 = __shfl_sync(kFull, mine.w10, src_lane);
     s.w11 = __shfl_sync(kFull, mine.w11, src_lane);
-    const int flags = (vf >> 24) & 0xF;
-    constexpr int kE = Tap<FT>::kElems, kR = Tap<FT>::kRegs;
-    static_assert(NV % kR == 0, "register vectors per tap must be a multiple of the registers one load fills");
-    const FT* __restrict__ p00 = fmap + (int64_t)(vf & 0xFFFFFF) * view_elems + o00 + lane * kE;
+    const uint32_t flags = lo & 0xFu;
+    const FT* __restrict__ p00 =
+        reinterpret_cast<const FT*>((uintptr_t)(((uint64_t)hi << 32) | (uint64_t)(lo & ~0xFu))) + lane * kE;
     const FT* __restrict__ p10 = p00 + row_elems;
-    if (flags == 0xF) {  // interior sample (the common case): unpredicated-on-validity loads
+    if (flags == 0xFu) {  // interior sample (the common case): unpredicated-on-validity loads
 #pragma unroll
         for (int l = 0; l < NV / kR; ++l) {
-            if ((l * 32 + lane) * kE < C) {
+            if (cmask & (1u << l)) {
                 Tap<FT>::load(&s.t00[l * kR], p00 + l * 32 * kE);
                 Tap<FT>::load(&s.t01[l * kR], p00 + C + l * 32 * kE);
                 Tap<FT>::load(&s.t10[l * kR], p10 + l * 32 * kE);
@@ -172,7 +183,7 @@ __device__ __forceinline__ void sample_issue(Sample<NV>& s, const SampleScalars&
     } else {  // border sample: taps outside the map read as zero (Appendix A `tap(y,x)`)
 #pragma unroll
         for (int l = 0; l < NV / kR; ++l) {
-            const bool cok = (l * 32 + lane) * kE < C;
+            const bool cok = (cmask >> l) & 1u;
 #pragma unroll
             for (int r = 0; r < kR; ++r) s.t00[l * kR + r] = s.t01[l * kR + r] = s.t10[l * kR + r] = s.t11[l * kR + r] = f4_zero();
             if (cok && (flags & 1)) Tap<FT>::load(&s.t00[l * kR], p00 + l * 32 * kE);
@@ -181,6 +192,15 @@ __device__ __forceinline__ void sample_issue(Sample<NV>& s, const SampleScalars&
             if (cok && (flags & 8)) Tap<FT>::load(&s.t11[l * kR], p10 + C + l * 32 * kE);
         }
     }
+}
+
+template <typename FT, int NV>
+__device__ __forceinline__ unsigned channel_mask(int C, int lane) {
+    unsigned m = 0u;
+#pragma unroll
+    for (int l = 0; l < NV / Tap<FT>::kRegs; ++l)
+        if ((l * 32 + lane) * Tap<FT>::kElems < C) m |= 1u << l;
+    return m;
 }
 
 template <int NV>
@@ -320,6 +340,7 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
     const FT* __restrict__ fmap = reinterpret_cast<const FT*>(p.fmap);
     const int64_t view_elems = (int64_t)p.Hf * p.Wf * p.C;
     const int row_elems = p.Wf * p.C;
+    const unsigned cmask = channel_mask<FT, NV>(p.C, lane);
 
     float4 sp_acc[NV];
 #pragma unroll
@@ -352,9 +373,7 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
             // lane r owns the (r0+r)-th visible view of this point (ascending view order) and computes that
             // sample's scalars once (re-projection needs no depth read: visibility is already in the mask)
             SampleScalars mine;
-            mine.view_flags = 0;
-            mine.o00 = 0;
-            mine.w00 = mine.w01 = mine.w10 = mine.w11 = 0.f;
+            scalars_clear(mine);
             {
                 int my_view = -1;
                 int rem = r0 + lane;
@@ -376,24 +395,24 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
                     const float4 q2 = ldg_f4(p.w2c + 12 * (int64_t)my_view + 8);
                     float my_u, my_w;
                     project_point(k4, q0, q1, q2, px, py, pz, p.z_near, my_u, my_w);
-                    mine = make_scalars(my_view, my_u, my_w, p.stride, p.Hf, p.Wf, p.C);
+                    mine = make_scalars<FT>(fmap, view_elems, my_view, my_u, my_w, p.stride, p.Hf, p.Wf, p.C);
                 }
             }
             const int n_round = min(32, n_total - r0);
             if (PREFETCH) {
-                sample_issue<NV, FT>(sa, mine, 0, fmap, view_elems, p.C, row_elems, lane);
+                sample_issue<NV, FT>(sa, mine, 0, p.C, row_elems, lane, cmask);
                 int sidx = 0;
                 while (true) {
-                    if (sidx + 1 < n_round) sample_issue<NV, FT>(sb, mine, sidx + 1, fmap, view_elems, p.C, row_elems, lane);
+                    if (sidx + 1 < n_round) sample_issue<NV, FT>(sb, mine, sidx + 1, p.C, row_elems, lane, cmask);
                     sample_accum<NV, FAST>(acc, sa);
                     if (++sidx >= n_round) break;
-                    if (sidx + 1 < n_round) sample_issue<NV, FT>(sa, mine, sidx + 1, fmap, view_elems, p.C, row_elems, lane);
+                    if (sidx + 1 < n_round) sample_issue<NV, FT>(sa, mine, sidx + 1, p.C, row_elems, lane, cmask);
                     sample_accum<NV, FAST>(acc, sb);
                     if (++sidx >= n_round) break;
                 }
             } else {  // wide rows (C > 512): one sample in flight, the tap rows alone fill the register file
                 for (int sidx = 0; sidx < n_round; ++sidx) {
-                    sample_issue<NV, FT>(sa, mine, sidx, fmap, view_elems, p.C, row_elems, lane);
+                    sample_issue<NV, FT>(sa, mine, sidx, p.C, row_elems, lane, cmask);
                     sample_accum<NV, FAST>(acc, sa);
                 }
             }
@@ -468,6 +487,7 @@ __global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePt
     const FT* __restrict__ fmap = reinterpret_cast<const FT*>(p.fmap);
     const int64_t view_elems = (int64_t)p.Hf * p.Wf * p.C;
     const int row_elems = p.Wf * p.C;
+    const unsigned cmask = channel_mask<FT, NV>(p.C, lane);
 
     float4 sp_acc[NV];
 #pragma unroll
@@ -539,9 +559,7 @@ __global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePt
         };
         auto make_view = [&](int vrel, int chunk, SampleScalars& sc, unsigned& vm) {
             const bool vis = own && ((__ldg(mw + chunk) >> (vrel & 31)) & 1u);
-            sc.view_flags = 0;
-            sc.o00 = 0;
-            sc.w00 = sc.w01 = sc.w10 = sc.w11 = 0.f;
+            scalars_clear(sc);
             if (vis) {
                 const int v = p.v_begin + vrel;
                 const float4 k4 = ldg_f4(p.K4 + 4 * (int64_t)v);
@@ -550,7 +568,7 @@ __global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePt
                 const float4 q2 = ldg_f4(p.w2c + 12 * (int64_t)v + 8);
                 float uu, ww;
                 project_point(k4, q0, q1, q2, mx, my, mz, p.z_near, uu, ww);
-                sc = make_scalars(v, uu, ww, p.stride, p.Hf, p.Wf, p.C);
+                sc = make_scalars<FT>(fmap, view_elems, v, uu, ww, p.stride, p.Hf, p.Wf, p.C);
             }
             vm = __ballot_sync(kFull, vis) & ((1u << kTileG) - 1u);
             // L1 prefetch of the (up to) 4 rows of each visible sample: lane = (row, 128-byte line)
@@ -561,11 +579,11 @@ __global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePt
             for (int j = 0; j < kTileG; ++j) {
                 if (!do_prefetch) break;
                 if (vm & (1u << j)) {
-                    const int vf = __shfl_sync(kFull, sc.view_flags, j);
-                    const int o00 = __shfl_sync(kFull, sc.o00, j);
-                    if (line_ok && ((vf >> (24 + prow)) & 1)) {
-                        const FT* a = fmap + (int64_t)(vf & 0xFFFFFF) * view_elems + o00 + (prow & 1) * p.C +
-                                      (prow >> 1) * row_elems + pline * line_elems;
+                    const uint32_t alo = __shfl_sync(kFull, sc.addr_lo, j);
+                    const uint32_t ahi = __shfl_sync(kFull, sc.addr_hi, j);
+                    if (line_ok && ((alo >> prow) & 1u)) {
+                        const FT* a = reinterpret_cast<const FT*>((uintptr_t)(((uint64_t)ahi << 32) | (uint64_t)(alo & ~0xFu))) +
+                                      (prow & 1) * p.C + (prow >> 1) * row_elems + pline * line_elems;
                         asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
                     }
                 }
@@ -582,19 +600,19 @@ __global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePt
             if (v_nxt >= 0) make_view(v_nxt, chunk_tmp, nxt, vm_nxt);
             if (DB && kTileG == 4) {
                 // static schedule, two samples in flight: A<-0, B<-1, use A, A<-2, use B, B<-3, use A, use B
-                if (vm_cur & 1u) sample_issue<NV, FT>(sa, cur, 0, fmap, view_elems, p.C, row_elems, lane);
-                if (vm_cur & 2u) sample_issue<NV, FT>(sb, cur, 1, fmap, view_elems, p.C, row_elems, lane);
+                if (vm_cur & 1u) sample_issue<NV, FT>(sa, cur, 0, p.C, row_elems, lane, cmask);
+                if (vm_cur & 2u) sample_issue<NV, FT>(sb, cur, 1, p.C, row_elems, lane, cmask);
                 if (vm_cur & 1u) sample_accum<NV, FAST>(acc[0], sa);
-                if (vm_cur & 4u) sample_issue<NV, FT>(sa, cur, 2, fmap, view_elems, p.C, row_elems, lane);
+                if (vm_cur & 4u) sample_issue<NV, FT>(sa, cur, 2, p.C, row_elems, lane, cmask);
                 if (vm_cur & 2u) sample_accum<NV, FAST>(acc[1], sb);
-                if (vm_cur & 8u) sample_issue<NV, FT>(sb, cur, 3, fmap, view_elems, p.C, row_elems, lane);
+                if (vm_cur & 8u) sample_issue<NV, FT>(sb, cur, 3, p.C, row_elems, lane, cmask);
                 if (vm_cur & 4u) sample_accum<NV, FAST>(acc[2], sa);
                 if (vm_cur & 8u) sample_accum<NV, FAST>(acc[3], sb);
             } else {  // rows were prefetched into L1 one view ahead: a single register buffer suffices
 #pragma unroll
                 for (int j = 0; j < kTileG; ++j) {
                     if (vm_cur & (1u << j)) {
-                        sample_issue<NV, FT>(sa, cur, j, fmap, view_elems, p.C, row_elems, lane);
+                        sample_issue<NV, FT>(sa, cur, j, p.C, row_elems, lane, cmask);
                         sample_accum<NV, FAST>(acc[j], sa);
                     }
                 }

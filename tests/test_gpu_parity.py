@@ -493,3 +493,62 @@ def test_scatter_mean_plan_cache_tracks_index_version():
     idx += 1
     src = torch.randn(4000, 16, generator=g)
     assert torch.equal(sd.scatter_mean(src.to(DEV), idx_d, dim=0).cpu(), so.scatter_mean_oracle(src, idx, dim=0))
+
+
+# ----------------------------------------------------------------------------------------------------
+# host-fed pipeline and C-ABI error behaviour
+# ----------------------------------------------------------------------------------------------------
+def test_scene_pipeline_matches_oracle_in_order():
+    """ScenePipeline (pinned host buffers -> H2D -> plan+lift -> D2H on three streams, 2-slot ring) must hand back,
+    in submission order, exactly what the oracle computes for each scene."""
+    from segdino3d_b200.pipeline import ScenePipeline
+    scenes, wants = [], []
+    for i in range(5):
+        sc = make_scene(n_points=3000 + 500 * i, n_views=6 + i, hd=60, wd=80, stride=4, channels=64, seed=50 + i,
+                        sp_target=20 + i)
+        a, c, _, _ = lo.lift_accumulate_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride)
+        feat = lo.lift_finalize_oracle(a, c)
+        wants.append((feat, c, so.scatter_mean_oracle(feat, sc.sp_ids, dim=0)))
+        h = {k: getattr(sc, k).pin_memory() for k in ("xyz", "K", "w2c", "depth", "fmap", "sp_ids")}
+        h["n_superpoints"], h["stride"] = sc.n_superpoints, sc.stride
+        scenes.append(h)
+    pipe = ScenePipeline(torch.device(DEV), depth=2)
+    n_out = 0
+    for (feat_h, cnt_h, sp_h), (feat, c, sp) in zip(pipe.run(iter(scenes)), wants):
+        assert not feat_h.is_cuda and feat_h.is_pinned()
+        assert torch.equal(feat_h, feat) and torch.equal(cnt_h, c)
+        assert rel_row_err(sp_h, sp, floor=0.1) <= 1e-5
+        n_out += 1
+    assert n_out == 5 and pipe.h2d_bytes > 0 and pipe.d2h_bytes > 0
+
+
+def test_c_abi_error_codes():
+    """Every entry returns a negative code and a message instead of crashing: bad shapes, small workspaces,
+    unsupported dtypes/widths (SURVEY 8b 'Errors')."""
+    import ctypes
+    from segdino3d_b200 import _lib
+    lib = _lib.load()
+    null = ctypes.c_void_p(0)
+    idx = torch.zeros(16, dtype=torch.int64, device=DEV)
+    perm = torch.zeros(16, dtype=torch.int32, device=DEV)
+    offs = torch.zeros(8, dtype=torch.int32, device=DEV)
+    ws = torch.zeros(64, dtype=torch.uint8, device=DEV)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.sd3d_sp_sort(P(idx), 16, 4, P(perm), P(offs), P(ws), 64, null) == _lib.ERR_ARG       # workspace too small
+    assert b"workspace" in lib.sd3d_last_error()
+    assert lib.sd3d_sp_sort(P(idx), -1, 4, P(perm), P(offs), P(ws), 64, null) == _lib.ERR_ARG
+    assert lib.sd3d_sp_max_tasks(16, 4, 0) == -1
+    f = torch.zeros(16, 6, device=DEV)
+    assert lib.sd3d_lift_finalize(P(f), P(perm), 16, 6, null) == _lib.ERR_ARG                        # C % 4 != 0
+    q = torch.zeros(8, 100, device=DEV)
+    out = torch.zeros(8, 8, device=DEV)
+    assert lib.sd3d_mask_logits(P(q), P(q), 8, 8, 100, _lib.BF16, P(out), 0.0, null, null) == _lib.ERR_UNSUPPORTED
+    assert lib.sd3d_mask_logits(P(q), P(q), 8, 8, 100, 7, P(out), 0.0, null, null) == _lib.ERR_UNSUPPORTED
+    assert lib.sd3d_mask_logits(null, P(q), 8, 8, 100, _lib.F32, P(out), 0.0, null, null) == _lib.ERR_ARG
+    # the python mirror turns codes into exceptions with the library's message
+    with pytest.raises(sd.Sd3dError, match="multiple of 4"):
+        sd.lift(torch.zeros(4, 3, device=DEV), torch.zeros(1, 4, device=DEV), torch.zeros(1, 3, 4, device=DEV),
+                torch.zeros(1, 8, 8, device=DEV), torch.zeros(1, 2, 2, 6, device=DEV))
+    # and the library is still usable afterwards
+    assert torch.equal(sd.scatter_mean(torch.ones(4, 4, device=DEV), torch.tensor([0, 0, 1, 1], device=DEV), dim=0).cpu(),
+                       torch.ones(2, 4))
