@@ -97,9 +97,10 @@ __global__ void attn_mask_fix_kernel(uint8_t* __restrict__ attn, int n, int S) {
 // tcgen05 / TMEM path (bf16 operands, fp32 accumulate)
 // ------------------------------------------------------------------------------------------------
 constexpr int kTcBM = 128;      // UMMA_M
-constexpr int kTcBN = 64;       // UMMA_N (TMEM columns)
-constexpr int kTcThreads = 128; // 4 warps <-> 4 x 32 TMEM lanes
+constexpr int kTcBN = 64;       // UMMA_N (TMEM columns per accumulator stage)
+constexpr int kTcThreads = 256; // 8 warps: warp w reads TMEM lanes 32*(w&3).. and column half (w>>2)
 constexpr int kTcKBlock = 64;   // bf16 elements per 128-byte swizzle row
+constexpr int kTcMaxTiles = 8;  // N tiles one CTA walks with its A operand resident in shared memory
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -135,148 +136,205 @@ __device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) 
 
 // Convert a [rows x d] fp32 row-major tile (rows beyond `valid_rows` are zero) to bf16 in the canonical
 // K-major SWIZZLE_128B layout: K-block kb (64 elements) is a [ROWS x 128 B] slab; 16-byte chunk j of row r
-// lands at r*128 + ((j ^ (r & 7)) << 4).
+// lands at r*128 + ((j ^ (r & 7)) << 4). Four chunks (8 x 128-bit loads) are in flight per thread.
 template <int ROWS>
 __device__ __forceinline__ void stage_operand(const float* __restrict__ g, int64_t row0, int valid_rows, int d,
                                               uint8_t* smem_tile) {
     const int chunks_per_row = d >> 3;
     const int total = ROWS * chunks_per_row;
-    for (int e = threadIdx.x; e < total; e += kTcThreads) {
-        const int r = e / chunks_per_row, kc = e % chunks_per_row;
-        float4 lo = f4_zero(), hi = f4_zero();
-        if (r < valid_rows) {
-            const float* src = g + (row0 + r) * (int64_t)d + kc * 8;
-            lo = ldg_f4(src);
-            hi = ldg_f4(src + 4);
+    constexpr int kU = 4;
+    for (int e0 = threadIdx.x; e0 < total; e0 += kTcThreads * kU) {
+        float4 lo[kU], hi[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int e = e0 + u * kTcThreads;
+            const int r = e / chunks_per_row, kc = e % chunks_per_row;
+            lo[u] = hi[u] = f4_zero();
+            if (e < total && r < valid_rows) {
+                const float* src = g + (row0 + r) * (int64_t)d + kc * 8;
+                lo[u] = ldg_f4(src);
+                hi[u] = ldg_f4(src + 4);
+            }
         }
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(lo.x, lo.y), p1 = __floats2bfloat162_rn(lo.z, lo.w);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(hi.x, hi.y), p3 = __floats2bfloat162_rn(hi.z, hi.w);
-        uint4 packed;
-        packed.x = *reinterpret_cast<uint32_t*>(&p0);
-        packed.y = *reinterpret_cast<uint32_t*>(&p1);
-        packed.z = *reinterpret_cast<uint32_t*>(&p2);
-        packed.w = *reinterpret_cast<uint32_t*>(&p3);
-        const int kb = kc >> 3, j = kc & 7;
-        uint8_t* dst = smem_tile + (size_t)kb * (ROWS * 128) + r * 128 + ((j ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = packed;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const int e = e0 + u * kTcThreads;
+            if (e >= total) continue;
+            const int r = e / chunks_per_row, kc = e % chunks_per_row;
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(lo[u].x, lo[u].y), p1 = __floats2bfloat162_rn(lo[u].z, lo[u].w);
+            __nv_bfloat162 p2 = __floats2bfloat162_rn(hi[u].x, hi[u].y), p3 = __floats2bfloat162_rn(hi[u].z, hi[u].w);
+            uint4 packed;
+            packed.x = *reinterpret_cast<uint32_t*>(&p0);
+            packed.y = *reinterpret_cast<uint32_t*>(&p1);
+            packed.z = *reinterpret_cast<uint32_t*>(&p2);
+            packed.w = *reinterpret_cast<uint32_t*>(&p3);
+            const int kb = kc >> 3, j = kc & 7;
+            uint8_t* dst = smem_tile + (size_t)kb * (ROWS * 128) + r * 128 + ((j ^ (r & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = packed;
+        }
     }
 }
 
+// epilogue of one 128 x 64 accumulator stage: warp w reads TMEM lanes 32*(w&3)..+31 (= accumulator rows) and the
+// 32 columns of half (w>>2); thread = one row x 32 columns -> 128-bit stores
+__device__ __forceinline__ void tc_epilogue(uint32_t tmem_stage, int m0, int n0, int n, int S, float* __restrict__ out,
+                                            float thr, uint8_t* __restrict__ attn) {
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int c0 = (warp >> 2) * 32;
+    const int gm = m0 + (warp & 3) * 32 + lane;
+    uint32_t v[32];
+    const uint32_t taddr = tmem_stage + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (gm < n) {
+        float* orow = out + (int64_t)gm * S + n0 + c0;
+        const bool full = (n0 + c0 + 32 <= S);
+        if (full && (S & 3) == 0) {  // 16-byte aligned row chunks: 128-bit stores
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(orow + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (attn) {
+                uint32_t* arow = reinterpret_cast<uint32_t*>(attn + (int64_t)gm * S + n0 + c0);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) w |= (__uint_as_float(v[j + k]) < thr ? 1u : 0u) << (8 * k);
+                    arow[j >> 2] = w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int gn = n0 + c0 + j;
+                if (gn < S) {
+                    const float val = __uint_as_float(v[j]);
+                    out[(int64_t)gm * S + gn] = val;
+                    if (attn) attn[(int64_t)gm * S + gn] = val < thr ? 1 : 0;  // thr is already a logit
+                }
+            }
+        }
+    }
+}
+
+// One CTA = one 128-row block of queries x `tiles` consecutive 64-column tiles of superpoints. The A operand is
+// converted to bf16 once and stays in shared memory; B tiles and TMEM accumulators are STAGES-deep, so with
+// STAGES == 2 the tensor core works on tile t (async, tcgen05.commit -> mbarrier) while all warps write out
+// tile t-1 and then stage tile t+1: one __syncthreads per tile.
+template <int STAGES>
 __global__ void __launch_bounds__(kTcThreads)
-    mask_logits_tc_kernel(const float* __restrict__ q, const float* __restrict__ mf, int n, int S, int d,
+    mask_logits_tc_kernel(const float* __restrict__ q, const float* __restrict__ mf, int n, int S, int d, int tiles,
                           float* __restrict__ out, float thr, uint8_t* __restrict__ attn) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment required by SWIZZLE_128B atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int kblocks = d / kTcKBlock;
+    const size_t a_bytes = (size_t)kblocks * (kTcBM * 128), b_bytes = (size_t)kblocks * (kTcBN * 128);
     uint8_t* sA = smem;
-    uint8_t* sB = smem + (size_t)kblocks * (kTcBM * 128);
-    __shared__ __align__(8) uint64_t s_bar;
+    uint8_t* sB = smem + a_bytes;
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_tmem;
 
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * kTcBN;
+    const int warp = threadIdx.x >> 5;
+    const int m0 = blockIdx.y * kTcBM;
+    const int nt0 = blockIdx.x * tiles;
+    const int n_tiles_total = (S + kTcBN - 1) / kTcBN;
+    const int my_tiles = min(tiles, n_tiles_total - nt0);
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)),
-                     "r"((uint32_t)kTcBN)
+                     "r"((uint32_t)(kTcBN * STAGES))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[1])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-
     stage_operand<kTcBM>(q, m0, min(kTcBM, n - m0), d, sA);
-    stage_operand<kTcBN>(mf, n0, min(kTcBN, S - n0), d, sB);
-    // generic-proxy smem writes -> visible to the async proxy (tensor core reads)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    stage_operand<kTcBN>(mf, (int64_t)nt0 * kTcBN, min(kTcBN, S - nt0 * kTcBN), d, sB);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> async proxy
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
+    const uint32_t idesc = make_idesc_bf16_f32(kTcBM, kTcBN);
+    const uint64_t descA0 = make_kmajor_sw128_desc(smem_u32(sA));
 
-    if (threadIdx.x == 0) {
-        const uint32_t idesc = make_idesc_bf16_f32(kTcBM, kTcBN);
-        const uint64_t descA0 = make_kmajor_sw128_desc(smem_u32(sA));
-        const uint64_t descB0 = make_kmajor_sw128_desc(smem_u32(sB));
-        for (int kb = 0; kb < kblocks; ++kb) {
+    for (int t = 0; t < my_tiles; ++t) {
+        const int st = (STAGES == 2) ? (t & 1) : 0;
+        // B tile t is staged and visible here (prologue / previous iteration + barrier): issue its MMAs
+        if (threadIdx.x == 0) {
+            const uint64_t descB0 = make_kmajor_sw128_desc(smem_u32(sB + (size_t)st * b_bytes));
+            const uint32_t tmem_d = tmem_base + (uint32_t)(st * kTcBN);
+            for (int kb = 0; kb < kblocks; ++kb) {
 #pragma unroll
-            for (int ks = 0; ks < kTcKBlock / 16; ++ks) {
-                const uint64_t da = descA0 + (uint64_t)(((uint32_t)kb * (kTcBM * 128) + ks * 32) >> 4);
-                const uint64_t db = descB0 + (uint64_t)(((uint32_t)kb * (kTcBN * 128) + ks * 32) >> 4);
-                const uint32_t accumulate = (kb | ks) ? 1u : 0u;
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "setp.ne.b32 p, %4, 0;\n\t"
-                    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                    :
-                    : "r"(tmem_base), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-                    : "memory");
-            }
-        }
-        // commit: arrives on the mbarrier when all MMAs above have completed (implies before_thread_sync)
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                         smem_u32(&s_bar))
-                     : "memory");
-    }
-    __syncwarp();
-    mbar_wait_parity(smem_u32(&s_bar), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // epilogue: warp w owns TMEM lanes [32w, 32w+32) == accumulator rows; thread = one row, 32 columns per load
-    const int gm = m0 + warp * 32 + lane;
-#pragma unroll
-    for (int c0 = 0; c0 < kTcBN; c0 += 32) {
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (gm < n) {
-            float* orow = out + (int64_t)gm * S + n0 + c0;
-            const bool full = (n0 + c0 + 32 <= S);
-            if (full && (S & 3) == 0) {  // 16-byte aligned row chunks: 128-bit stores
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4*>(orow + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                if (attn) {
-                    uint32_t* arow = reinterpret_cast<uint32_t*>(attn + (int64_t)gm * S + n0 + c0);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        uint32_t w = 0;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) w |= (__uint_as_float(v[j + k]) < thr ? 1u : 0u) << (8 * k);
-                        arow[j >> 2] = w;
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int gn = n0 + c0 + j;
-                    if (gn < S) {
-                        const float val = __uint_as_float(v[j]);
-                        out[(int64_t)gm * S + gn] = val;
-                        if (attn) attn[(int64_t)gm * S + gn] = val < thr ? 1 : 0;  // thr is already a logit
-                    }
+                for (int ks = 0; ks < kTcKBlock / 16; ++ks) {
+                    const uint64_t da = descA0 + (uint64_t)(((uint32_t)kb * (kTcBM * 128) + ks * 32) >> 4);
+                    const uint64_t db = descB0 + (uint64_t)(((uint32_t)kb * (kTcBN * 128) + ks * 32) >> 4);
+                    const uint32_t accumulate = (kb | ks) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\t"
+                        "setp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                        :
+                        : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+                        : "memory");
                 }
             }
+            // commit: arrives on the stage's mbarrier when the MMAs above have completed
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             smem_u32(&s_bar[st]))
+                         : "memory");
         }
+        __syncwarp();
+        if (STAGES == 2) {
+            // while the tensor core works on tile t: write out tile t-1, then stage tile t+1
+            if (t > 0) {
+                mbar_wait_parity(smem_u32(&s_bar[st ^ 1]), (uint32_t)(((t - 1) >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                tc_epilogue(tmem_base + (uint32_t)((st ^ 1) * kTcBN), m0, (nt0 + t - 1) * kTcBN, n, S, out, thr, attn);
+            }
+            if (t + 1 < my_tiles) {  // stage st^1 is free: its MMAs (tile t-1) were waited for above
+                stage_operand<kTcBN>(mf, (int64_t)(nt0 + t + 1) * kTcBN, min(kTcBN, S - (nt0 + t + 1) * kTcBN), d,
+                                     sB + (size_t)(st ^ 1) * b_bytes);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+        } else {
+            mbar_wait_parity(smem_u32(&s_bar[0]), (uint32_t)(t & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc_epilogue(tmem_base, m0, (nt0 + t) * kTcBN, n, S, out, thr, attn);
+            if (t + 1 < my_tiles) {
+                stage_operand<kTcBN>(mf, (int64_t)(nt0 + t + 1) * kTcBN, min(kTcBN, S - (nt0 + t + 1) * kTcBN), d, sB);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // TMEM stage read out + next B tile staged, for every warp
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    if (STAGES == 2 && my_tiles > 0) {  // drain: the last tile
+        const int t = my_tiles - 1, st = t & 1;
+        mbar_wait_parity(smem_u32(&s_bar[st]), (uint32_t)((t >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tc_epilogue(tmem_base + (uint32_t)(st * kTcBN), m0, (nt0 + t) * kTcBN, n, S, out, thr, attn);
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
     if (warp == 0) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kTcBN)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"((uint32_t)(kTcBN * STAGES))
                      : "memory");
     }
 }
@@ -317,19 +375,31 @@ extern "C" int sd3d_mask_logits(const float* q, const float* mf, int n, int S, i
                       d);
             return SD3D_ERR_UNSUPPORTED;
         }
-        const size_t smem = (size_t)(d / kTcKBlock) * (kTcBM + kTcBN) * 128 + 1024;
+        const int stages = d <= 256 ? 2 : 1;  // two B / TMEM stages fit beside a 128 x 256 bf16 A tile
+        const size_t smem = (size_t)(d / kTcKBlock) * (kTcBM + stages * kTcBN) * 128 + 1024;
         static bool attr_set = false;  // idempotent attribute; benign race
         if (!attr_set) {
-            cudaError_t e = cudaFuncSetAttribute(mask_logits_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaError_t e = cudaFuncSetAttribute(mask_logits_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)(512 / kTcKBlock * (kTcBM + kTcBN) * 128 + 1024));
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(mask_logits_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(256 / kTcKBlock * (kTcBM + 2 * kTcBN) * 128 + 1024));
             if (e != cudaSuccess) {
                 set_error("sd3d_mask_logits: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
                 return SD3D_ERR_CUDA;
             }
             attr_set = true;
         }
-        dim3 grid((S + kTcBN - 1) / kTcBN, (n + kTcBM - 1) / kTcBM);
-        mask_logits_tc_kernel<<<grid, kTcThreads, smem, stream>>>(q, mf, n, S, d, out, thr, attn_mask);
+        // N tiles per CTA: keep >= ~2 CTAs per SM in the grid, at most kTcMaxTiles per CTA
+        const int n_tiles = (S + kTcBN - 1) / kTcBN, m_blocks = (n + kTcBM - 1) / kTcBM;
+        int tiles = (int)(((int64_t)n_tiles * m_blocks) / (2 * (int64_t)num_sms()));
+        if (tiles < 1) tiles = 1;
+        if (tiles > kTcMaxTiles) tiles = kTcMaxTiles;
+        dim3 grid((n_tiles + tiles - 1) / tiles, m_blocks);
+        if (stages == 2)
+            mask_logits_tc_kernel<2><<<grid, kTcThreads, smem, stream>>>(q, mf, n, S, d, tiles, out, thr, attn_mask);
+        else
+            mask_logits_tc_kernel<1><<<grid, kTcThreads, smem, stream>>>(q, mf, n, S, d, tiles, out, thr, attn_mask);
     } else {
         set_error("sd3d_mask_logits: precision code %d unsupported (SD3D_F32 | SD3D_BF16)", precision);
         return SD3D_ERR_UNSUPPORTED;
