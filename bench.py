@@ -331,6 +331,7 @@ def run_ours(args):
 
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
+        traffic, traffic_src = ncu_traffic(args)
         ach = b_gather / (lift_ms * 1e-3) / 1e9
         line = {
             "metric": "scenes/s lifting+SP-pool", "value": value, "unit": "scenes/s", "n_gpus": world,
@@ -344,7 +345,7 @@ def run_ours(args):
                        "projection_overlaps_plan": not args.no_overlap},
             "points_per_s": value * n, "host_us_per_step": host_us,
             "roofline": {"bound": "hbm", "kernel": "gather_kernel (bilinear gather + view mean + run partials)",
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": b_gather, "kernel_ms": lift_ms, "peak_source": peak_src,
                          "path_algorithmic_bytes": b_path,
                          "path_frac": b_path / (ms_per_step * 1e-3) / 1e9 / peak},
@@ -358,6 +359,27 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ncu_traffic(args):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one gather_kernel launch, from the committed `ncu --set full`
+    capture of this same command (profiles/rNN_ncu_gather_summary.txt). Only valid for the configuration it was taken
+    on (cfg2, default kernel), otherwise null."""
+    import glob
+    import re
+    if args.workload != "cfg2" or args.variant != 0 or args.run != 32:
+        return None, "no ncu capture for this configuration"
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
+                                          "r*_ncu_gather_summary.txt")))
+    if not files:
+        return None, "profiles/ has no gather capture"
+    unit = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for ln in open(files[-1]):
+        m = re.match(r"dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", ln)
+        if m:
+            tot += float(m.group(2)) * unit[m.group(3)]
+    return (int(tot), os.path.relpath(files[-1], os.path.dirname(os.path.abspath(__file__)))) if tot else (None, "parse")
 
 
 def main():
