@@ -57,11 +57,12 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("SD3D_LIB", LIB_PATH)  # developer override: an experimental build of the same ABI
+    if not os.path.exists(path):
         raise Sd3dError(
-            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
+            f"{path} not found: the CUDA extension is not built. Run `python -c 'import __graft_entry__ as g; "
             f"g.build()'` (or `make -C segdino3d_b200/csrc`). There is no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)  # AttributeError here = ABI drift between header and library
         fn.restype = res

@@ -23,6 +23,10 @@ namespace sd3d {
 constexpr int kLiftThreads = 128;
 constexpr int kLiftWarps = kLiftThreads / 32;
 
+#ifndef SD3D_SCALAR_BLEND
+#define SD3D_SCALAR_BLEND 0  // 1 = scalar FMUL/FADD blend (the pre-FMUL2 code, kept for A/B timing)
+#endif
+
 struct LiftParams {
     const float* xyz;
     int64_t N;
@@ -34,7 +38,7 @@ struct LiftParams {
     int Hd, Wd;
     const void* fmap;
     int Hf, Wf, C;
-    float stride, tau, z_near;
+    float stride, inv_stride, tau, z_near;  // inv_stride = 1/stride when stride is a power of two, else 0
     int accumulate, finalize;
     int by_pos;  // rows of out / count are indexed by processing position instead of point id
     const int32_t* order;
@@ -50,6 +54,10 @@ struct LiftParams {
     int32_t S;
     int run;
     float* partials;
+    // K1 -> K2 hand-off (workspace): per point, one record per visible view of this call, in ascending view order
+    int4* recs;       // [N][n_views]; only the first nvis[pid] entries of a row are written
+    int32_t* nvis;    // [N]
+    int n_views;
 };
 
 // One 128-bit load per lane per tap row: 4 fp32 channels, or 8 fp16 / bf16 channels (= two float4 registers).
@@ -67,7 +75,9 @@ template <>
 struct Tap<__half> {
     static constexpr int kElems = 8, kRegs = 2;
     __device__ __forceinline__ static void load(float4* dst, const __half* p) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+        decode(dst, __ldg(reinterpret_cast<const uint4*>(p)));
+    }
+    __device__ __forceinline__ static void decode(float4* dst, const uint4 raw) {
         const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
         const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
         const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&raw.z));
@@ -80,7 +90,9 @@ template <>
 struct Tap<__nv_bfloat16> {
     static constexpr int kElems = 8, kRegs = 2;
     __device__ __forceinline__ static void load(float4* dst, const __nv_bfloat16* p) {
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p));
+        decode(dst, __ldg(reinterpret_cast<const uint4*>(p)));
+    }
+    __device__ __forceinline__ static void decode(float4* dst, const uint4 raw) {
         dst[0] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
                              __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
         dst[1] = make_float4(__uint_as_float(raw.z << 16), __uint_as_float(raw.z & 0xffff0000u),
@@ -103,6 +115,55 @@ __device__ __forceinline__ float blend1(float acc, float w00, float w01, float w
     f = __fadd_rn(f, __fmul_rn(w10, t10));
     f = __fadd_rn(f, __fmul_rn(w11, t11));
     return __fadd_rn(acc, f);
+}
+
+// ---- packed fp32x2 arithmetic (sm_100 FMUL2 / FADD2 / FFMA2): two channels per instruction, each half rounded exactly
+// like the scalar __fmul_rn / __fadd_rn, so the blend issues half as many FP instructions and stays bit-exact.
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (single rounding; unlike the scalar .rn forms, and
+// even through the __fmul2_rn/__fadd2_rn intrinsics), which would break Appendix A. The adds that consume a product
+// are therefore written as fma(product, 1.0, addend) with the 1.0 read from constant memory, which ptxas cannot see
+// through: product*1 is exact, so the result is rn(product + addend), the same as the unfused add.
+typedef unsigned long long u64;
+__constant__ float2 c_one2 = {1.0f, 1.0f};
+__device__ __forceinline__ u64 pk2(float a, float b) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpk2(u64 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+struct Weights2 {
+    u64 w00, w01, w10, w11, one;
+};
+// two channels of blend1: f = ((w00*t00 + w01*t01) + w10*t10) + w11*t11 ; acc = acc + f
+template <bool FAST>
+__device__ __forceinline__ void blend2(float& ax, float& ay, const Weights2& w, float t00x, float t00y, float t01x,
+                                       float t01y, float t10x, float t10y, float t11x, float t11y) {
+    u64 r;
+    if (FAST) {
+        r = fma2(w.w11, pk2(t11x, t11y),
+                 fma2(w.w10, pk2(t10x, t10y), fma2(w.w01, pk2(t01x, t01y), fma2(w.w00, pk2(t00x, t00y), pk2(ax, ay)))));
+    } else {
+        u64 f = fma2(mul2(w.w01, pk2(t01x, t01y)), w.one, mul2(w.w00, pk2(t00x, t00y)));
+        f = fma2(mul2(w.w10, pk2(t10x, t10y)), w.one, f);
+        f = fma2(mul2(w.w11, pk2(t11x, t11y)), w.one, f);
+        r = add2(pk2(ax, ay), f);  // neither operand is a bare product: nothing to contract
+    }
+    unpk2(r, ax, ay);
 }
 
 // One bilinear sample in flight: the four tap rows (this lane's channel vectors) + the weights.
@@ -128,44 +189,101 @@ __device__ __forceinline__ void scalars_clear(SampleScalars& r) {
     r.w00 = r.w01 = r.w10 = r.w11 = 0.f;
 }
 
-template <typename FT>
-__device__ __forceinline__ SampleScalars make_scalars(const FT* fmap, int64_t view_elems, int view, float u, float w,
-                                                      float stride, int Hf, int Wf, int C) {
-    SampleScalars r;
-    const float uf = __fsub_rn(__fdiv_rn(__fadd_rn(u, 0.5f), stride), 0.5f);
-    const float wf = __fsub_rn(__fdiv_rn(__fadd_rn(w, 0.5f), stride), 0.5f);
+// Appendix A lines `uf = ...` .. `w11 = ...`: tap origin, bilinear weights, which taps lie inside the map
+struct TapGeom {
+    int x0, y0;
+    float ax, ay;
+    float w00, w01, w10, w11;
+    uint32_t flags;  // bit0..3 = t00,t01,t10,t11 inside the map
+};
+// inv_stride > 0: stride is a power of two, so x / stride == x * inv_stride bit for bit (a pure exponent shift)
+__device__ __forceinline__ TapGeom tap_geometry(float u, float w, float stride, float inv_stride, int Hf, int Wf) {
+    TapGeom r;
+    float uf, wf;
+    if (inv_stride > 0.f) {
+        uf = __fsub_rn(__fmul_rn(__fadd_rn(u, 0.5f), inv_stride), 0.5f);
+        wf = __fsub_rn(__fmul_rn(__fadd_rn(w, 0.5f), inv_stride), 0.5f);
+    } else {
+        uf = __fsub_rn(__fdiv_rn(__fadd_rn(u, 0.5f), stride), 0.5f);
+        wf = __fsub_rn(__fdiv_rn(__fadd_rn(w, 0.5f), stride), 0.5f);
+    }
     const float x0f = floorf(uf), y0f = floorf(wf);
     const float ax = __fsub_rn(uf, x0f), ay = __fsub_rn(wf, y0f);
-    const int x0 = (int)x0f, y0 = (int)y0f;
+    r.x0 = (int)x0f;
+    r.y0 = (int)y0f;
+    r.ax = ax;
+    r.ay = ay;
     const float omx = __fsub_rn(1.0f, ax), omy = __fsub_rn(1.0f, ay);
     r.w00 = __fmul_rn(omx, omy);
     r.w01 = __fmul_rn(ax, omy);
     r.w10 = __fmul_rn(omx, ay);
     r.w11 = __fmul_rn(ax, ay);
-    const bool okx0 = (x0 >= 0) && (x0 < Wf), okx1 = (x0 + 1 >= 0) && (x0 + 1 < Wf);
-    const bool oky0 = (y0 >= 0) && (y0 < Hf), oky1 = (y0 + 1 >= 0) && (y0 + 1 < Hf);
-    const uint32_t flags = (uint32_t)(oky0 && okx0) | ((uint32_t)(oky0 && okx1) << 1) | ((uint32_t)(oky1 && okx0) << 2) |
-                           ((uint32_t)(oky1 && okx1) << 3);
-    const int64_t elem = (int64_t)view * view_elems + ((int64_t)y0 * Wf + x0) * C;
+    const bool okx0 = (r.x0 >= 0) && (r.x0 < Wf), okx1 = (r.x0 + 1 >= 0) && (r.x0 + 1 < Wf);
+    const bool oky0 = (r.y0 >= 0) && (r.y0 < Hf), oky1 = (r.y0 + 1 >= 0) && (r.y0 + 1 < Hf);
+    r.flags = (uint32_t)(oky0 && okx0) | ((uint32_t)(oky0 && okx1) << 1) | ((uint32_t)(oky1 && okx0) << 2) |
+              ((uint32_t)(oky1 && okx1) << 3);
+    return r;
+}
+
+template <typename FT>
+__device__ __forceinline__ SampleScalars make_scalars(const FT* fmap, int64_t view_elems, int view, float u, float w,
+                                                      float stride, float inv_stride, int Hf, int Wf, int C) {
+    SampleScalars r;
+    const TapGeom g = tap_geometry(u, w, stride, inv_stride, Hf, Wf);
+    r.w00 = g.w00;
+    r.w01 = g.w01;
+    r.w10 = g.w10;
+    r.w11 = g.w11;
+    const int64_t elem = (int64_t)view * view_elems + ((int64_t)g.y0 * Wf + g.x0) * C;
     const uint64_t addr = (uint64_t)(reinterpret_cast<uintptr_t>(fmap) + elem * (int64_t)sizeof(FT));
-    r.addr_lo = (uint32_t)addr | flags;
+    r.addr_lo = (uint32_t)addr | g.flags;
     r.addr_hi = (uint32_t)(addr >> 32);
     return r;
 }
 
 // issue the 4*NV 128-bit loads of sample `src_lane` (no use of the data here -> they stay in flight).
 // cmask: bit l set = this lane's l-th 128-bit vector lies inside the C channels (hoisted out of the sample loop).
+// Sample record written by K1 for every visible (point, view): {pixel index of tap (y0, x0) in the [V, Hf, Wf] map
+// (may lie outside the map by one row/column), tap-valid flags, ax, ay}. K2 rebuilds the packed tap address and the
+// four weights from it with the same operations as make_scalars (w = products of ax, ay, 1-ax, 1-ay).
+__device__ __forceinline__ int4 make_record(const TapGeom& g, float ax, float ay, int view, int Hf, int Wf) {
+    return make_int4((view * Hf + g.y0) * Wf + g.x0, (int)g.flags, __float_as_int(ax), __float_as_int(ay));
+}
+template <typename FT>
+__device__ __forceinline__ SampleScalars scalars_from_record(const int4 rec, const FT* fmap, int C) {
+    SampleScalars r;
+    const float ax = __int_as_float(rec.z), ay = __int_as_float(rec.w);
+    const float omx = __fsub_rn(1.0f, ax), omy = __fsub_rn(1.0f, ay);
+    r.w00 = __fmul_rn(omx, omy);
+    r.w01 = __fmul_rn(ax, omy);
+    r.w10 = __fmul_rn(omx, ay);
+    r.w11 = __fmul_rn(ax, ay);
+    const uint64_t addr = (uint64_t)(reinterpret_cast<uintptr_t>(fmap) + (int64_t)rec.x * C * (int64_t)sizeof(FT));
+    r.addr_lo = (uint32_t)addr | (uint32_t)rec.y;
+    r.addr_hi = (uint32_t)(addr >> 32);
+    return r;
+}
+
+template <int NV, typename FT>
+__device__ __forceinline__ void sample_issue_loads(Sample<NV>& s, uint32_t lo, uint32_t hi, int C, int row_elems, int lane,
+                                                   unsigned cmask);
 template <int NV, typename FT>
 __device__ __forceinline__ void sample_issue(Sample<NV>& s, const SampleScalars& mine, int src_lane, int C,
                                              int row_elems, int lane, unsigned cmask) {
-    constexpr int kE = Tap<FT>::kElems, kR = Tap<FT>::kRegs;
-    static_assert(NV % kR == 0, "register vectors per tap must be a multiple of the registers one load fills");
     const uint32_t lo = __shfl_sync(kFull, mine.addr_lo, src_lane);
     const uint32_t hi = __shfl_sync(kFull, mine.addr_hi, src_lane);
     s.w00 = __shfl_sync(kFull, mine.w00, src_lane);
     s.w01 = __shfl_sync(kFull, mine.w01, src_lane);
     s.w10 = __shfl_sync(kFull, mine.w10, src_lane);
     s.w11 = __shfl_sync(kFull, mine.w11, src_lane);
+    sample_issue_loads<NV, FT>(s, lo, hi, C, row_elems, lane, cmask);
+}
+// the loads of one sample given its (warp-uniform) packed tap address + flags
+template <int NV, typename FT>
+__device__ __forceinline__ void sample_issue_loads(Sample<NV>& s, uint32_t lo, uint32_t hi, int C, int row_elems, int lane,
+                                                   unsigned cmask) {
+    constexpr int kE = Tap<FT>::kElems, kR = Tap<FT>::kRegs;
+    static_assert(NV % kR == 0, "register vectors per tap must be a multiple of the registers one load fills");
     const uint32_t flags = lo & 0xFu;
     const FT* __restrict__ p00 =
         reinterpret_cast<const FT*>((uintptr_t)(((uint64_t)hi << 32) | (uint64_t)(lo & ~0xFu))) + lane * kE;
@@ -211,6 +329,7 @@ __device__ __forceinline__ void sample_clear(Sample<NV>& s) {
 
 template <int NV, bool FAST>
 __device__ __forceinline__ void sample_accum(float4 (&acc)[NV], const Sample<NV>& s) {
+#if SD3D_SCALAR_BLEND
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         acc[k].x = blend1<FAST>(acc[k].x, s.w00, s.w01, s.w10, s.w11, s.t00[k].x, s.t01[k].x, s.t10[k].x, s.t11[k].x);
@@ -218,6 +337,21 @@ __device__ __forceinline__ void sample_accum(float4 (&acc)[NV], const Sample<NV>
         acc[k].z = blend1<FAST>(acc[k].z, s.w00, s.w01, s.w10, s.w11, s.t00[k].z, s.t01[k].z, s.t10[k].z, s.t11[k].z);
         acc[k].w = blend1<FAST>(acc[k].w, s.w00, s.w01, s.w10, s.w11, s.t00[k].w, s.t01[k].w, s.t10[k].w, s.t11[k].w);
     }
+#else
+    Weights2 w;
+    w.w00 = pk2(s.w00, s.w00);
+    w.w01 = pk2(s.w01, s.w01);
+    w.w10 = pk2(s.w10, s.w10);
+    w.w11 = pk2(s.w11, s.w11);
+    w.one = pk2(c_one2.x, c_one2.y);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        blend2<FAST>(acc[k].x, acc[k].y, w, s.t00[k].x, s.t00[k].y, s.t01[k].x, s.t01[k].y, s.t10[k].x, s.t10[k].y,
+                     s.t11[k].x, s.t11[k].y);
+        blend2<FAST>(acc[k].z, acc[k].w, w, s.t00[k].z, s.t00[k].w, s.t01[k].z, s.t01[k].w, s.t10[k].z, s.t10[k].w,
+                     s.t11[k].z, s.t11[k].w);
+    }
+#endif
 }
 
 // Appendix A lines `xc = ...` .. `w = ...` for one (point, view): returns zc, writes u / w
@@ -236,78 +370,78 @@ __device__ __forceinline__ float project_point(const float4 k4, const float4 r0,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K1: projection + depth-visibility (step a-1). One warp per point, LANE = VIEW within a 32-view chunk;
-// __ballot_sync packs the predicate into one mask word per (point, chunk). Integer outputs only.
+// K1: projection + depth-visibility (step a-1). LANE = POINT: a thread walks the views of its point, four at a time
+// (four independent depth reads in flight), so every lane is busy whatever the number of views, camera matrices are
+// warp-uniform loads, and no shuffles are needed: the thread builds its point's visibility mask words and appends
+// one sample record per visible view (ascending view order) for K2. Integer outputs + records only.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kProjThreads = 256;
-constexpr int kProjWarps = kProjThreads / 32;
-constexpr int kProjPts = 4;  // points per warp: 4 independent depth reads in flight per lane
+constexpr int kProjThreads = 64;
+constexpr int kProjViews = 4;  // views per round: 4 independent depth reads in flight per lane
 
 __global__ void __launch_bounds__(kProjThreads) project_kernel(const LiftParams p, uint32_t* __restrict__ masks,
                                                                int nchunks) {
-    const int lane = lane_id();
-    const int64_t p0 = ((int64_t)blockIdx.x * kProjWarps + (threadIdx.x >> 5)) * kProjPts;
-    if (p0 >= p.N) return;
-    // the warp's points are consecutive in the processing order: spatial neighbours read neighbouring
-    // depth pixels (same 32-byte sectors) instead of one random DRAM sector per (point, view)
-    int64_t pidv[kProjPts];
-    float px[kProjPts], py[kProjPts], pz[kProjPts];
-#pragma unroll
-    for (int j = 0; j < kProjPts; ++j) {
-        const int64_t pos = min(p0 + j, p.N - 1);
-        pidv[j] = p.order ? (int64_t)p.order[pos] : pos;
-        px[j] = __ldg(p.xyz + 3 * pidv[j]);
-        py[j] = __ldg(p.xyz + 3 * pidv[j] + 1);
-        pz[j] = __ldg(p.xyz + 3 * pidv[j] + 2);
-    }
+    const int64_t pos = (int64_t)blockIdx.x * kProjThreads + threadIdx.x;
+    if (pos >= p.N) return;
+    // consecutive lanes = consecutive points of the processing order: with a plan, spatial neighbours read
+    // neighbouring depth pixels (same 32-byte sectors); the optional [V, N] maps are written coalesced
+    const int64_t pid = p.order ? (int64_t)p.order[pos] : pos;
+    const float px = __ldg(p.xyz + 3 * pid), py = __ldg(p.xyz + 3 * pid + 1), pz = __ldg(p.xyz + 3 * pid + 2);
     const int64_t depth_elems = (int64_t)p.Hd * p.Wd;
     const float wd_f = (float)p.Wd, hd_f = (float)p.Hd;
-    for (int c = 0; c < nchunks; ++c) {
-        const int v = p.v_begin + c * 32 + lane;
-        const bool vok = v < p.v_end;
-        float4 k4 = f4_zero(), r0 = f4_zero(), r1 = f4_zero(), r2 = f4_zero();
-        if (vok) {
-            k4 = ldg_f4(p.K4 + 4 * (int64_t)v);
-            r0 = ldg_f4(p.w2c + 12 * (int64_t)v);
-            r1 = ldg_f4(p.w2c + 12 * (int64_t)v + 4);
-            r2 = ldg_f4(p.w2c + 12 * (int64_t)v + 8);
-        }
-        float zc[kProjPts], d[kProjPts];
-        int cand[kProjPts];
+    int4* __restrict__ recs = p.recs + pid * p.n_views;
+    uint32_t* __restrict__ mrow = masks + pid * nchunks;
+    int nv = 0;        // visible views so far = slot of the next record
+    uint32_t m = 0u;   // mask word being filled
+    for (int v0 = p.v_begin; v0 < p.v_end; v0 += kProjViews) {
+        float zc[kProjViews], d[kProjViews], us[kProjViews], ws[kProjViews];
+        int cand[kProjViews];
 #pragma unroll
-        for (int j = 0; j < kProjPts; ++j) {  // phase 1: project, issue the depth reads
-            cand[j] = -1;
-            d[j] = 0.f;
-            zc[j] = 0.f;
-            if (vok && p0 + j < p.N) {
-                float uu, ww;
-                zc[j] = project_point(k4, r0, r1, r2, px[j], py[j], pz[j], p.z_near, uu, ww);
-                if (zc[j] > p.z_near) {
-                    const float uif = floorf(__fadd_rn(uu, 0.5f));
-                    const float wif = floorf(__fadd_rn(ww, 0.5f));
+        for (int t = 0; t < kProjViews; ++t) {  // phase 1: project, issue the depth reads (camera loads are uniform)
+            const int v = v0 + t;
+            cand[t] = -1;
+            d[t] = zc[t] = us[t] = ws[t] = 0.f;
+            if (v < p.v_end) {
+                const float4 k4 = ldg_f4(p.K4 + 4 * (int64_t)v);
+                const float4 r0 = ldg_f4(p.w2c + 12 * (int64_t)v);
+                const float4 r1 = ldg_f4(p.w2c + 12 * (int64_t)v + 4);
+                const float4 r2 = ldg_f4(p.w2c + 12 * (int64_t)v + 8);
+                zc[t] = project_point(k4, r0, r1, r2, px, py, pz, p.z_near, us[t], ws[t]);
+                if (zc[t] > p.z_near) {
+                    const float uif = floorf(__fadd_rn(us[t], 0.5f));
+                    const float wif = floorf(__fadd_rn(ws[t], 0.5f));
                     if (uif >= 0.f && uif < wd_f && wif >= 0.f && wif < hd_f) {
-                        cand[j] = (int)wif * p.Wd + (int)uif;
+                        cand[t] = (int)wif * p.Wd + (int)uif;
                         if (p.depth_u16)
-                            d[j] = __fmul_rn((float)__ldg(reinterpret_cast<const uint16_t*>(p.depth) +
-                                                          (int64_t)v * depth_elems + cand[j]),
+                            d[t] = __fmul_rn((float)__ldg(reinterpret_cast<const uint16_t*>(p.depth) +
+                                                          (int64_t)v * depth_elems + cand[t]),
                                              0.001f);
                         else
-                            d[j] = __ldg(reinterpret_cast<const float*>(p.depth) + (int64_t)v * depth_elems + cand[j]);
+                            d[t] = __ldg(reinterpret_cast<const float*>(p.depth) + (int64_t)v * depth_elems + cand[t]);
                     }
                 }
             }
         }
 #pragma unroll
-        for (int j = 0; j < kProjPts; ++j) {  // phase 2: depth test, pack the predicate
-            const bool visible = cand[j] >= 0 && d[j] > 0.f && fabsf(__fsub_rn(d[j], zc[j])) <= p.tau;
-            if (vok && p0 + j < p.N) {
-                if (p.pix_idx) p.pix_idx[(int64_t)v * p.N + pidv[j]] = visible ? cand[j] : -1;
-                if (p.vis) p.vis[(int64_t)v * p.N + pidv[j]] = visible ? 1 : 0;
+        for (int t = 0; t < kProjViews; ++t) {  // phase 2: depth test, mask bit, sample record
+            const int v = v0 + t;
+            if (v < p.v_end) {
+                const bool visible = cand[t] >= 0 && d[t] > 0.f && fabsf(__fsub_rn(d[t], zc[t])) <= p.tau;
+                if (p.pix_idx) p.pix_idx[(int64_t)v * p.N + pid] = visible ? cand[t] : -1;
+                if (p.vis) p.vis[(int64_t)v * p.N + pid] = visible ? 1 : 0;
+                const int bit = (v - p.v_begin) & 31;
+                if (visible) {
+                    const TapGeom g = tap_geometry(us[t], ws[t], p.stride, p.inv_stride, p.Hf, p.Wf);
+                    recs[nv++] = make_record(g, g.ax, g.ay, v, p.Hf, p.Wf);
+                    m |= 1u << bit;
+                }
+                if (bit == 31 || v == p.v_end - 1) {
+                    mrow[(v - p.v_begin) >> 5] = m;
+                    m = 0u;
+                }
             }
-            const unsigned m = __ballot_sync(kFull, visible);
-            if (lane == 0 && p0 + j < p.N) masks[pidv[j] * nchunks + c] = m;
         }
     }
+    p.nvis[pid] = nv;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -338,7 +472,6 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
         end = min(start + (int64_t)p.run, p.N);
     }
     const FT* __restrict__ fmap = reinterpret_cast<const FT*>(p.fmap);
-    const int64_t view_elems = (int64_t)p.Hf * p.Wf * p.C;
     const int row_elems = p.Wf * p.C;
     const unsigned cmask = channel_mask<FT, NV>(p.C, lane);
 
@@ -352,11 +485,8 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
     for (int64_t i = start + warp; i < end; i += kLiftWarps) {
         const int32_t pid = p.order ? p.order[i] : (int32_t)i;
         const int64_t orow = p.by_pos ? i : (int64_t)pid;  // output row
-        const float px = __ldg(p.xyz + 3 * (int64_t)pid), py = __ldg(p.xyz + 3 * (int64_t)pid + 1),
-                    pz = __ldg(p.xyz + 3 * (int64_t)pid + 2);
-        const uint32_t* __restrict__ mw = masks + (int64_t)pid * nchunks;
-        int n_total = 0;
-        for (int c = 0; c < nchunks; ++c) n_total += __popc(__ldg(mw + c));
+        const int n_total = nchunks > 0 ? p.nvis[pid] : 0;
+        const int4* __restrict__ recs = p.recs + (int64_t)pid * p.n_views;
         float4 acc[NV];
 #pragma unroll
         for (int k = 0; k < NV; ++k) acc[k] = f4_zero();
@@ -370,34 +500,11 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
             }
         }
         for (int r0 = 0; r0 < n_total; r0 += 32) {
-            // lane r owns the (r0+r)-th visible view of this point (ascending view order) and computes that
-            // sample's scalars once (re-projection needs no depth read: visibility is already in the mask)
+            // lane r owns the (r0+r)-th visible view of this point (ascending view order): K1 left its sample
+            // record (tap pixel, flags, fractional offsets) in the workspace
             SampleScalars mine;
             scalars_clear(mine);
-            {
-                int my_view = -1;
-                int rem = r0 + lane;
-                if (rem < n_total) {
-                    for (int c = 0; c < nchunks; ++c) {
-                        const uint32_t m = __ldg(mw + c);
-                        const int pc = __popc(m);
-                        if (rem < pc) {
-                            my_view = p.v_begin + c * 32 + (int)__fns(m, 0, rem + 1);
-                            break;
-                        }
-                        rem -= pc;
-                    }
-                }
-                if (my_view >= 0) {
-                    const float4 k4 = ldg_f4(p.K4 + 4 * (int64_t)my_view);
-                    const float4 q0 = ldg_f4(p.w2c + 12 * (int64_t)my_view);
-                    const float4 q1 = ldg_f4(p.w2c + 12 * (int64_t)my_view + 4);
-                    const float4 q2 = ldg_f4(p.w2c + 12 * (int64_t)my_view + 8);
-                    float my_u, my_w;
-                    project_point(k4, q0, q1, q2, px, py, pz, p.z_near, my_u, my_w);
-                    mine = make_scalars<FT>(fmap, view_elems, my_view, my_u, my_w, p.stride, p.Hf, p.Wf, p.C);
-                }
-            }
+            if (r0 + lane < n_total) mine = scalars_from_record<FT>(recs[r0 + lane], fmap, p.C);
             const int n_round = min(32, n_total - r0);
             if (PREFETCH) {
                 sample_issue<NV, FT>(sa, mine, 0, p.C, row_elems, lane, cmask);
@@ -568,7 +675,7 @@ __global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePt
                 const float4 q2 = ldg_f4(p.w2c + 12 * (int64_t)v + 8);
                 float uu, ww;
                 project_point(k4, q0, q1, q2, mx, my, mz, p.z_near, uu, ww);
-                sc = make_scalars<FT>(fmap, view_elems, v, uu, ww, p.stride, p.Hf, p.Wf, p.C);
+                sc = make_scalars<FT>(fmap, view_elems, v, uu, ww, p.stride, p.inv_stride, p.Hf, p.Wf, p.C);
             }
             vm = __ballot_sync(kFull, vis) & ((1u << kTileG) - 1u);
             // L1 prefetch of the (up to) 4 rows of each visible sample: lane = (row, 128-byte line)
@@ -776,6 +883,12 @@ static int dispatch_gather(const LiftParams& p, const uint32_t* masks, int nchun
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+// 1/stride if stride is a (normal) power of two, else 0: then dividing and multiplying by the reciprocal agree bit for bit
+static float pow2_reciprocal(float stride) {
+    int e = 0;
+    const float m = frexpf(stride, &e);
+    return (m == 0.5f && e > -100 && e < 100) ? 1.0f / stride : 0.f;
+}
 
 }  // namespace sd3d
 
@@ -784,7 +897,9 @@ using namespace sd3d;
 extern "C" size_t sd3d_lift_workspace_bytes(int64_t N, int n_views, int C, int64_t max_tasks) {
     if (N < 0 || n_views < 0 || C < 0 || max_tasks < 0) return 0;
     const size_t nchunks = (size_t)(n_views + 31) / 32;
-    return align_up((size_t)max_tasks * C * sizeof(float), 256) + align_up((size_t)N * nchunks * sizeof(uint32_t), 256) + 256;
+    // run partials | visibility masks | visible-view counts | sample records (16 B per (point, view) slot)
+    return align_up((size_t)max_tasks * C * sizeof(float), 256) + align_up((size_t)N * nchunks * sizeof(uint32_t), 256) +
+           align_up((size_t)N * sizeof(int32_t), 256) + align_up((size_t)N * n_views * sizeof(int4), 256) + 256;
 }
 
 extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin,
@@ -848,16 +963,19 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
     uint32_t* masks = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ws) +
                                                   align_up((size_t)max_tasks * C * sizeof(float), 256));
     LiftParams p;
+    p.nvis = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(masks) + align_up((size_t)N * nchunks * sizeof(uint32_t), 256));
+    p.recs = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(p.nvis) + align_up((size_t)N * sizeof(int32_t), 256));
+    p.n_views = n_views;
     p.xyz = xyz; p.N = N; p.K4 = K4; p.w2c = w2c; p.v_begin = view_begin; p.v_end = view_end;
     p.depth = depth; p.depth_u16 = depth_dtype == SD3D_U16; p.Hd = Hd; p.Wd = Wd;
-    p.fmap = fmap; p.Hf = Hf; p.Wf = Wf; p.C = C; p.stride = stride; p.tau = tau; p.z_near = z_near;
+    p.fmap = fmap; p.Hf = Hf; p.Wf = Wf; p.C = C; p.stride = stride; p.inv_stride = pow2_reciprocal(stride); p.tau = tau; p.z_near = z_near;
     p.accumulate = accumulate; p.finalize = finalize; p.by_pos = (variant & 1024) ? 1 : 0; p.order = order; p.out = out_feat; p.count = count;
     p.pix_idx = pix_idx; p.vis = vis; p.pool = pool ? 1 : 0; p.seg_offsets = seg_offsets;
     p.task_offsets = task_offsets; p.task_seg = task_seg; p.S = (int32_t)S; p.run = run;
     p.partials = reinterpret_cast<float*>(ws);
     const int64_t n_tasks = pool ? max_tasks : ceil_div64(N, run);
     if (do_project && nchunks > 0)
-        project_kernel<<<(unsigned)ceil_div64(N, kProjWarps * kProjPts), kProjThreads, 0, stream>>>(p, masks, nchunks);
+        project_kernel<<<(unsigned)ceil_div64(N, kProjThreads), kProjThreads, 0, stream>>>(p, masks, nchunks);
     if (!do_gather) return check_launch("sd3d_lift(project)");
     int rc;
     switch (fmap_dtype) {

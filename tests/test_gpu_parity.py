@@ -220,6 +220,15 @@ def test_lift_channel_widths(channels):
     _check_lift(sc)
 
 
+@pytest.mark.parametrize("stride", [2, 3, 5, 6, 16])
+def test_lift_strides_power_of_two_and_not(stride):
+    """power-of-two strides take the multiply-by-reciprocal shortcut (bit-identical to the division of Appendix A),
+    the others the IEEE division."""
+    sc = make_scene(n_points=3000, n_views=9, hd=60, wd=80, stride=stride, channels=64, seed=40 + stride, sp_target=30)
+    _check_lift(sc)
+    _check_lift(sc, variant=2)
+
+
 @pytest.mark.parametrize("variant", [0, 2, 6, 26])
 @pytest.mark.parametrize("run", [32, 80])
 def test_lift_kernel_variants_bit_exact(variant, run):
