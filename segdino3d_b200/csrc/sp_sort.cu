@@ -20,6 +20,8 @@
 // Keys outside [0,S) are mapped to the extra key S ("trash"), which sorts last.
 #include <cooperative_groups.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -49,7 +51,7 @@ static SortGeom sort_geom(int64_t N, int64_t S) {
     // the passes are latency-bound at ScanNet sizes: ~2048 items per block keeps the per-warp serial chain of
     // the stable scatter short (8 steps) while the [bins][blocks] matrix still fits one CTA's shared memory;
     // <= kFusedMaxBlocks blocks so that the pass can run as one cooperative kernel
-    const int64_t by_size = N / 2048 > 8 ? N / 2048 : 8;
+    const int64_t by_size = N / 1024 > 8 ? N / 1024 : 8;
     if (nb_cap > by_size) nb_cap = (int)by_size;
     if (nb_cap > 128) nb_cap = 128;
     int64_t t = ceil_div64(N > 0 ? N : 1, nb_cap);
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(kSortThreads)
     }
 }
 
-// One radix pass as ONE cooperative kernel: hist -> grid.sync -> scan (block 0) -> grid.sync -> scatter.
+// One radix pass as ONE cooperative kernel: hist -> grid.sync -> per-block column prefix + bin scan -> scatter.
 // At ScanNet sizes every phase is a few microseconds of latency, so the two kernel boundaries (launch gap +
 // tail + ramp) cost more than the work; the grid barrier replaces them. Same arithmetic as the three
 // separate kernels (which remain the fallback when the grid cannot be co-resident).
@@ -244,7 +246,7 @@ __global__ void __launch_bounds__(kSortThreads)
                             int32_t* __restrict__ vals_out, const float* __restrict__ xyz, float inv_cell,
                             uint32_t* __restrict__ cell_out, int32_t* __restrict__ seg_offsets) {
     extern __shared__ int32_t s_dyn[];
-    __shared__ int32_t s_rowbase[1 << kMaxDigitBits];
+    __shared__ int32_t s_rowbase[1 << kMaxDigitBits], s_pre[1 << kMaxDigitBits];
     __shared__ int32_t s_warp[kSortWarps];
     cg::grid_group grid = cg::this_grid();
     const int bins = 1 << bits;
@@ -259,65 +261,54 @@ __global__ void __launch_bounds__(kSortThreads)
         atomicAdd(&s_dyn[(key >> shift) & (bins - 1)], 1);
     }
     __syncthreads();
-    for (int i = tid; i < bins; i += kSortThreads) hist[(int64_t)i * nb + blockIdx.x] = s_dyn[i];
+    for (int i = tid; i < bins; i += kSortThreads) hist[(int64_t)blockIdx.x * bins + i] = s_dyn[i];  // [nb][bins]
     grid.sync();
-    // ---- phase 2: block 0 scans the [bins][nb] matrix (staged in its shared memory)
-    if (blockIdx.x == 0) {
-        const int total = bins * nb;
-        for (int i = tid; i < total; i += kSortThreads) s_dyn[i] = hist[i];
-        __syncthreads();
-        for (int row = warp; row < bins; row += kSortWarps) {
-            int32_t* r = s_dyn + row * nb;
-            int32_t carry = 0;
-            for (int c0 = 0; c0 < nb; c0 += 32) {
-                const int col = c0 + lane;
-                const int32_t v = col < nb ? r[col] : 0;
-                int32_t inc = v;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int32_t n = __shfl_up_sync(kFull, inc, o);
-                    if (lane >= o) inc += n;
-                }
-                if (col < nb) r[col] = carry + inc - v;
-                carry += __shfl_sync(kFull, inc, 31);
-            }
-            if (lane == 0) s_rowbase[row] = carry;
+    // ---- phase 2: EVERY block derives what it needs from the [nb][bins] matrix (L2-resident, coalesced over bins):
+    // per bin, the count in the blocks before it (its offset inside the bin) and the bin total; then a block-local
+    // exclusive scan of the totals gives the bin bases. No serial scan CTA, no second grid-wide barrier.
+    for (int b = tid; b < bins; b += kSortThreads) {
+        int32_t pre = 0, tot = 0;
+        for (int k = 0; k < nb; ++k) {
+            const int32_t v = hist[(int64_t)k * bins + b];
+            tot += v;
+            if (k < (int)blockIdx.x) pre += v;
         }
-        __syncthreads();
-        {  // exclusive scan of the row totals: 4 consecutive bins per thread (bins <= 1024)
-            int32_t t[4], tsum = 0;
+        s_pre[b] = pre;
+        s_rowbase[b] = tot;
+    }
+    __syncthreads();
+    {  // exclusive scan of the bin totals: 4 consecutive bins per thread (bins <= 1024)
+        int32_t t[4], tsum = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int b = tid * 4 + k;
-                t[k] = b < bins ? s_rowbase[b] : 0;
-                tsum += t[k];
-            }
-            int32_t inc = tsum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int32_t n = __shfl_up_sync(kFull, inc, o);
-                if (lane >= o) inc += n;
-            }
-            if (lane == 31) s_warp[warp] = inc;
-            __syncthreads();
-            int32_t wbase = 0;
-            for (int w = 0; w < warp; ++w) wbase += s_warp[w];
-            int32_t excl = wbase + inc - tsum;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int b = tid * 4 + k;
-                if (b < bins) s_rowbase[b] = excl;
-                excl += t[k];
-            }
+        for (int k = 0; k < 4; ++k) {
+            const int b = tid * 4 + k;
+            t[k] = b < bins ? s_rowbase[b] : 0;
+            tsum += t[k];
         }
+        int32_t inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t n = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
-        for (int i = tid; i < total; i += kSortThreads) hist[i] = s_dyn[i] + s_rowbase[i / nb];
-        if (seg_offsets != nullptr) {
-            for (int s = tid; s <= S; s += kSortThreads) seg_offsets[s] = s_rowbase[s];
-            if (tid == 0) seg_offsets[S + 1] = (int32_t)N;
+        int32_t wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+        int32_t excl = wbase + inc - tsum;
+        __syncthreads();  // everyone has read its totals before they are overwritten with the bases
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int b = tid * 4 + k;
+            if (b < bins) s_rowbase[b] = excl;
+            excl += t[k];
         }
     }
-    grid.sync();
+    __syncthreads();
+    if (blockIdx.x == 0 && seg_offsets != nullptr) {
+        for (int sg = tid; sg <= S; sg += kSortThreads) seg_offsets[sg] = s_rowbase[sg];
+        if (tid == 0) seg_offsets[S + 1] = (int32_t)N;
+    }
     // ---- phase 3: stable scatter (identical to radix_scatter_kernel)
     int32_t* s_cnt = s_dyn;  // [kSortWarps][bins]
     for (int i = tid; i < bins * kSortWarps; i += kSortThreads) s_cnt[i] = 0;
@@ -332,7 +323,7 @@ __global__ void __launch_bounds__(kSortThreads)
     }
     __syncthreads();
     for (int b = tid; b < bins; b += kSortThreads) {
-        int32_t run = hist[(int64_t)b * nb + blockIdx.x];
+        int32_t run = s_rowbase[b] + s_pre[b];
 #pragma unroll
         for (int w = 0; w < kSortWarps; ++w) {
             const int32_t c = s_cnt[w * bins + b];
@@ -675,7 +666,7 @@ static int run_sort(const int64_t* idx, const float* xyz, float inv_cell, int64_
         const size_t sm_hist = (size_t)bins * sizeof(int32_t);
         const size_t sm_scat = (size_t)bins * kSortWarps * sizeof(int32_t);
         const size_t sm_scan = (size_t)bins * g.nb * sizeof(int32_t);
-        const size_t sm_fused = sm_scan > sm_scat ? sm_scan : sm_scat;
+        const size_t sm_fused = sm_scat;  // [kSortWarps][bins] counters (>= the [bins] histogram of phase 1)
         bool fused_done = false;
         if (g.nb <= kFusedMaxBlocks) {
             int32_t S32 = (int32_t)S;
@@ -741,6 +732,24 @@ static int run_tasks(const int32_t* seg_offsets, const int32_t* perm, const floa
     }
     sp_tasks_kernel<<<1, 1024, smem, stream>>>(seg_offsets, perm, xyz, nseg, run, task_offsets, task_seg, max_tasks);
     return SD3D_OK;
+}
+
+// Side streams owned by the library (per device, a few of them so that plans of different caller streams do not
+// serialise behind each other); never destroyed.
+static cudaStream_t plan_side_stream() {
+    constexpr int kMaxDev = 64, kPerDev = 4;
+    static std::mutex mu;
+    static cudaStream_t pool[kMaxDev][kPerDev] = {};
+    static unsigned next[kMaxDev] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    const unsigned k = next[dev]++ % kPerDev;
+    if (pool[dev][k] == nullptr && cudaStreamCreateWithFlags(&pool[dev][k], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        pool[dev][k] = nullptr;
+    }
+    return pool[dev][k];
 }
 
 }  // namespace sd3d
@@ -823,8 +832,25 @@ extern "C" int sd3d_sp_plan(const int64_t* idx, const float* xyz, int64_t N, int
     }
     rc = run_sort(idx, xyz, 1.0f / cell, N, S, perm, seg_offsets, w, stream);
     if (rc != SD3D_OK) return rc;
-    rc = run_tasks(seg_offsets, perm, xyz, S, run, task_offsets, task_seg, max_tasks, stream);
+    // The task table (one latency-bound CTA) and the refinement (one CTA per superpoint) both depend only on the
+    // sort: fork the task table onto a library-owned side stream and join before returning, so they overlap.
+    cudaStream_t side = plan_side_stream();
+    cudaEvent_t e_fork = nullptr, e_join = nullptr;
+    if (side != nullptr && cudaEventCreateWithFlags(&e_fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&e_join, cudaEventDisableTiming) == cudaSuccess) {
+        cudaEventRecord(e_fork, stream);
+        cudaStreamWaitEvent(side, e_fork, 0);
+        rc = run_tasks(seg_offsets, perm, xyz, S, run, task_offsets, task_seg, max_tasks, side);
+        cudaEventRecord(e_join, side);
+        sp_refine_kernel<<<(unsigned)(S + 1), kSortThreads, 0, stream>>>(perm, w.cell, seg_offsets, w.tmp_perm, w.tmp_key, N, order);
+        cudaStreamWaitEvent(stream, e_join, 0);
+    } else {
+        cudaGetLastError();
+        rc = run_tasks(seg_offsets, perm, xyz, S, run, task_offsets, task_seg, max_tasks, stream);
+        sp_refine_kernel<<<(unsigned)(S + 1), kSortThreads, 0, stream>>>(perm, w.cell, seg_offsets, w.tmp_perm, w.tmp_key, N, order);
+    }
+    if (e_fork) cudaEventDestroy(e_fork);  // released by the runtime once the recorded work has completed
+    if (e_join) cudaEventDestroy(e_join);
     if (rc != SD3D_OK) return rc;
-    sp_refine_kernel<<<(unsigned)(S + 1), kSortThreads, 0, stream>>>(perm, w.cell, seg_offsets, w.tmp_perm, w.tmp_key, N, order);
     return check_launch("sd3d_sp_plan");
 }
