@@ -414,8 +414,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="replicas", choices=["replicas", "viewshard"])
-    ap.add_argument("--exchange", default="reduce_scatter", choices=["allreduce", "reduce_scatter", "overlap"])
-    ap.add_argument("--chunks", type=int, default=4, help="point chunks of the overlapped view-sharded exchange")
+    ap.add_argument("--exchange", default="reduce_scatter", choices=["allreduce", "reduce_scatter", "p2p"])
     ap.add_argument("--rotate", type=int, default=4, help="distinct scenes cycled through (defeats L2 residency)")
     ap.add_argument("--run", type=int, default=32, help="points per warp run")
     ap.add_argument("--variant", type=int, default=0, help="points-per-warp group (0=default, 1/2/4/8)")

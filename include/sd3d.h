@@ -104,15 +104,18 @@ int sd3d_sp_mean(const float* src, const int32_t* perm, const int32_t* seg_offse
  * Fused pooling (pool != 0): needs order/seg_offsets/task_offsets/task_seg/run from the plan entries
  *   above and finalize != 0; the kernel leaves one partial row per run at the start of ws
  *   and sd3d_sp_combine(ws, ...) then yields sp_out[S,C] = scatter_mean(out_feat, idx).
- * ws: sd3d_lift_workspace_bytes(N, view_end-view_begin, C, pool ? max_tasks : 0) bytes: the per-point view
- *   bit-masks written by the projection kernel (+ the run partials when pool != 0, at offset 0).
+ * ws: sd3d_lift_workspace_bytes(N, view_end-view_begin, C, pool ? max_tasks : 0) bytes: what the projection kernel
+ *   hands to the gather kernel -- per-point view bit-masks, visible-view counts and one 16-byte sample record per
+ *   visible (point, view) in [N][views] slots -- plus the run partials when pool != 0 (at offset 0). A
+ *   projection-only call and the matching gather-only call must pass the same N, view range, C and max_tasks.
  * variant: bit 0 = contract the bilinear blend into FFMA (not bit-exact to Appendix A, <= 1e-6 rel.);
  *   bit 1 = view-synchronous tile gather kernel instead of the point-streaming one (same results; bits 2-4
  *   tune it: 4 = register double buffer, 8 = no per-view barrier, 16 = no L1 prefetch);
  *   bit 8 (256) = run the projection kernel only, bit 9 (512) = run the gather kernel only on the masks a
  *   previous projection-only call left in the same ws (per-kernel timing, stream overlap);
  *   bit 10 (1024) = rows of out_feat / count are indexed by processing position i (point order[i]) instead
- *   of by point id: chunks of the processing order are then contiguous (multi-GPU chunked exchange).
+ *   of by point id (what sd3d_lift_push does for its staging rows);
+ *   bits 5/6 (32/64) = default gather compiled for 5 / 3 resident CTAs per SM (tuning points).
  * --------------------------------------------------------------------------------------------- */
 size_t sd3d_lift_workspace_bytes(int64_t N, int n_views, int C, int64_t max_tasks);
 int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin, int view_end,
@@ -125,6 +128,34 @@ int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, in
 /* second half of the fused pooling: sp_out[s,:] = (sum of the run partials of s, in run order) / max(|s|,1) */
 int sd3d_sp_combine(const void* partials, const int32_t* task_offsets, const int32_t* seg_offsets, int64_t S, int C,
                     int run, float* sp_out, void* stream);
+
+/* ---- view-sharded multi-GPU lifting with the exchange fused into the gather ("fuse the exchange with
+ * the producing kernel"; the reference is single-GPU, evaluation/evaluate_3d.py:45). Rank `src_rank` lifts its views
+ * [view_begin, view_end) for ALL points and stores the un-normalised row of processing position i (= order[i]) and
+ * its visible count straight into the staging buffers of the rank that owns the position:
+ *     owner = i / rows_per_rank,  slot = src_rank * rows_per_rank + (i % rows_per_rank)
+ *     peer_sum[owner][slot, :] = sum over this rank's visible views,  peer_count[owner][slot] = their number
+ * peer_sum[r] / peer_count[r] are device pointers valid on THIS device for rank r's staging buffers
+ * ([n_ranks][rows_per_rank][C] f32 and [n_ranks][rows_per_rank] i32; peer-mapped with sd3d_ipc_import below, the
+ * rank's own buffer directly). Stores to other ranks travel over NVLink while the kernel keeps gathering; no
+ * collective moves feature rows. Same workspace as sd3d_lift. After a cross-rank barrier, sd3d_push_reduce on every
+ * rank sums its slots in ascending rank order and divides by max(total count, 1). */
+int sd3d_lift_push(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin, int view_end,
+                   const void* depth, int depth_dtype, int Hd, int Wd, const void* fmap, int fmap_dtype, int Hf, int Wf,
+                   int C, float stride, float tau, float z_near, const int32_t* order, int run, void* ws, size_t ws_bytes,
+                   int n_ranks, int src_rank, int64_t rows_per_rank, void* const* peer_sum /*host array*/,
+                   void* const* peer_count /*host array*/, int variant, void* stream);
+int sd3d_push_reduce(const float* stage_sum, const int32_t* stage_count, int n_ranks, int64_t rows_per_rank,
+                     int64_t rows /*<= rows_per_rank: rows this rank owns*/, int C, float* feat /*[rows,C]*/,
+                     int32_t* count /*[rows]*/, void* stream);
+
+/* staging memory that other processes can map (one process per GPU): plain cudaMalloc + CUDA IPC handles (64 bytes,
+ * exchanged by the caller, e.g. torch.distributed.all_gather). The library never frees imported mappings itself. */
+int sd3d_peer_alloc(size_t bytes, void** ptr);
+int sd3d_peer_free(void* ptr);
+int sd3d_ipc_export(void* ptr, uint8_t* handle64);
+int sd3d_ipc_import(const uint8_t* handle64, void** ptr);
+int sd3d_ipc_close(void* ptr);
 
 /* feat = sum / (float)max(count,1) in place (Appendix A `feat_l`); used after the multi-GPU all-reduce */
 int sd3d_lift_finalize(float* sum_inout, const int32_t* count, int64_t N, int C, void* stream);

@@ -37,6 +37,18 @@ SYMBOLS = {
                           c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,           # seg_off S task_off task_seg max_tasks run
                           c_void_p, c_size_t, c_int, c_int, c_void_p]),                    # ws ws_bytes pool variant stream
     "sd3d_sp_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    "sd3d_lift_push": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,   # xyz N K4 w2c V vb ve
+                               c_void_p, c_int, c_int, c_int,                                # depth dtype Hd Wd
+                               c_void_p, c_int, c_int, c_int, c_int,                         # fmap dtype Hf Wf C
+                               c_float, c_float, c_float,                                    # stride tau z_near
+                               c_void_p, c_int, c_void_p, c_size_t,                          # order run ws ws_bytes
+                               c_int, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p]), # ranks src rows sums cnts variant stream
+    "sd3d_push_reduce": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    "sd3d_peer_alloc": (c_int, [c_size_t, c_void_p]),
+    "sd3d_peer_free": (c_int, [c_void_p]),
+    "sd3d_ipc_export": (c_int, [c_void_p, c_void_p]),
+    "sd3d_ipc_import": (c_int, [c_void_p, c_void_p]),
+    "sd3d_ipc_close": (c_int, [c_void_p]),
     "sd3d_lift_finalize": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "sd3d_scale_mean": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     "sd3d_sp_expand_mask": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),

@@ -16,6 +16,8 @@
 //   * per-point accumulators stay in registers across all views; one coalesced streaming store per point;
 //   * optional fused superpoint pooling: the finalised rows of the run are summed in registers and written
 //     as ONE partial row per run (no atomics); sp_combine_kernel adds the partials in run order.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace sd3d {
@@ -26,6 +28,8 @@ constexpr int kLiftWarps = kLiftThreads / 32;
 #ifndef SD3D_SCALAR_BLEND
 #define SD3D_SCALAR_BLEND 0  // 1 = scalar FMUL/FADD blend (the pre-FMUL2 code, kept for A/B timing)
 #endif
+
+constexpr int kMaxPeers = 16;
 
 struct LiftParams {
     const float* xyz;
@@ -55,6 +59,12 @@ struct LiftParams {
     int run;
     float* partials;
     // K1 -> K2 hand-off (workspace): per point, one record per visible view of this call, in ascending view order
+    // push mode (view-sharded multi-GPU, sd3d_lift_push): the un-normalised row of processing position i goes to rank
+    // i / rows_per_rank, slot [src_rank][i % rows_per_rank] of that rank's staging buffers (peer-mapped device memory)
+    int n_peers, src_rank, task_rot;
+    int64_t rows_per_rank;
+    float* peer_out[kMaxPeers];
+    int32_t* peer_cnt[kMaxPeers];
     int4* recs;       // [N][n_views]; only the first nvis[pid] entries of a row are written
     int32_t* nvis;    // [N]
     int n_views;
@@ -453,7 +463,7 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(const LiftParams 
 // rows are in flight while sample i is blended).
 // ---------------------------------------------------------------------------------------------------
 template <int NV, typename FT, bool FAST, bool PREFETCH, int MINB>
-__global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftParams p, const uint32_t* __restrict__ masks,
+__global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const __grid_constant__ LiftParams p, const uint32_t* __restrict__ masks,
                                                               int nchunks) {
     __shared__ float4 s_red[kLiftWarps][NV * 32];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -467,7 +477,9 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
         start = (int64_t)p.seg_offsets[seg] + (task - p.task_offsets[seg]) * (int64_t)p.run;
         end = min(start + (int64_t)p.run, (int64_t)p.seg_offsets[seg + 1]);
     } else {
-        start = task * (int64_t)p.run;
+        // push mode rotates the chunk order by rank (task_rot) so that at any moment the ranks store into
+        // DIFFERENT owners: a balanced all-to-all instead of an incast on one rank's NVLink ingress
+        start = (int64_t)((blockIdx.x + (unsigned)p.task_rot) % gridDim.x) * p.run;
         if (start >= p.N) return;
         end = min(start + (int64_t)p.run, p.N);
     }
@@ -524,17 +536,25 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const LiftPa
                 }
             }
         }
+        float* out_row = p.out + orow * p.C;
+        int32_t* cnt_dst = p.count + orow;
+        if (p.n_peers > 0) {  // push mode: store straight into the owner rank's staging slot (NVLink peer store)
+            const int owner = (int)(i / p.rows_per_rank);
+            const int64_t slot = (int64_t)p.src_rank * p.rows_per_rank + (i - (int64_t)owner * p.rows_per_rank);
+            out_row = p.peer_out[owner] + slot * p.C;
+            cnt_dst = p.peer_cnt[owner] + slot;
+        }
         const float denom = (float)max(cnt, 1);
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const int c = chan_of<FT>(k, lane);
             if (c < p.C) {
                 const float4 o = p.finalize ? f4_div(acc[k], denom) : acc[k];
-                st_cs_f4(p.out + orow * p.C + c, o);
+                st_cs_f4(out_row + c, o);
                 sp_acc[k] = f4_add(sp_acc[k], o);
             }
         }
-        if (lane == 0) p.count[orow] = cnt;
+        if (lane == 0) *cnt_dst = cnt;
     }
     if (p.pool && seg < p.S) {  // uniform per CTA
 #pragma unroll
@@ -902,14 +922,36 @@ extern "C" size_t sd3d_lift_workspace_bytes(int64_t N, int n_views, int C, int64
            align_up((size_t)N * sizeof(int32_t), 256) + align_up((size_t)N * n_views * sizeof(int4), 256) + 256;
 }
 
-extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin,
-                         int view_end, const void* depth, int depth_dtype, int Hd, int Wd, const void* fmap,
-                         int fmap_dtype, int Hf, int Wf, int C, float stride, float tau, float z_near, int accumulate,
-                         int finalize, const int32_t* order, float* out_feat, int32_t* count, int32_t* pix_idx,
-                         uint8_t* vis, const int32_t* seg_offsets, int64_t S, const int32_t* task_offsets,
-                         const int32_t* task_seg, int64_t max_tasks, int run, void* ws, size_t ws_bytes, int pool_,
-                         int variant, void* stream_) {
+struct PushTargets {
+    int n_ranks, src_rank;
+    int64_t rows_per_rank;
+    void* const* outs;  // [n_ranks] float* staging [n_ranks][rows_per_rank][C] of every rank (peer-mapped)
+    void* const* cnts;  // [n_ranks] int32* staging [n_ranks][rows_per_rank]
+};
+
+static int lift_impl(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin,
+                     int view_end, const void* depth, int depth_dtype, int Hd, int Wd, const void* fmap,
+                     int fmap_dtype, int Hf, int Wf, int C, float stride, float tau, float z_near, int accumulate,
+                     int finalize, const int32_t* order, float* out_feat, int32_t* count, int32_t* pix_idx,
+                     uint8_t* vis, const int32_t* seg_offsets, int64_t S, const int32_t* task_offsets,
+                     const int32_t* task_seg, int64_t max_tasks, int run, void* ws, size_t ws_bytes, int pool_,
+                     int variant, void* stream_, const PushTargets* push) {
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (push != nullptr) {
+        if (push->n_ranks < 1 || push->n_ranks > kMaxPeers || push->src_rank < 0 || push->src_rank >= push->n_ranks ||
+            push->rows_per_rank <= 0 || push->rows_per_rank * push->n_ranks < N || push->outs == nullptr ||
+            push->cnts == nullptr || accumulate || finalize || pool_ || (order == nullptr && (variant & 256) == 0) ||
+            (variant & 2)) {
+            set_error("sd3d_lift_push: needs 1..%d ranks, rows_per_rank * ranks >= N, a processing order, and "
+                      "accumulate = finalize = pool = 0 (default gather kernel)", kMaxPeers);
+            return SD3D_ERR_ARG;
+        }
+        for (int r = 0; r < push->n_ranks; ++r)
+            if (push->outs[r] == nullptr || push->cnts[r] == nullptr || !aligned16(push->outs[r])) {
+                set_error("sd3d_lift_push: staging pointer of rank %d is null or misaligned", r);
+                return SD3D_ERR_ARG;
+            }
+    }
     if (N < 0 || V < 0 || view_begin < 0 || view_end > V || view_begin > view_end || Hd <= 0 || Wd <= 0 || Hf <= 0 ||
         Wf <= 0 || C <= 0 || !(stride > 0.f) || N >= (int64_t(1) << 31) - 64 || (int64_t)Hd * Wd >= (int64_t(1) << 31)) {
         set_error("sd3d_lift: bad shape N=%lld V=%d views=[%d,%d) depth=%dx%d fmap=%dx%dx%d stride=%g", (long long)N,
@@ -928,7 +970,7 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
         set_error("sd3d_lift: depth dtype code %d unsupported", depth_dtype);
         return SD3D_ERR_UNSUPPORTED;
     }
-    if (N > 0 && (xyz == nullptr || out_feat == nullptr || count == nullptr)) {
+    if (N > 0 && (xyz == nullptr || (push == nullptr && (out_feat == nullptr || count == nullptr)))) {
         set_error("sd3d_lift: null xyz/out_feat/count");
         return SD3D_ERR_ARG;
     }
@@ -966,10 +1008,28 @@ extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const flo
     p.nvis = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(masks) + align_up((size_t)N * nchunks * sizeof(uint32_t), 256));
     p.recs = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(p.nvis) + align_up((size_t)N * sizeof(int32_t), 256));
     p.n_views = n_views;
+    p.n_peers = 0;
+    p.src_rank = 0;
+    p.task_rot = 0;
+    p.rows_per_rank = 1;
+    for (int r = 0; r < kMaxPeers; ++r) {
+        p.peer_out[r] = nullptr;
+        p.peer_cnt[r] = nullptr;
+    }
+    if (push != nullptr) {
+        p.n_peers = push->n_ranks;
+        p.src_rank = push->src_rank;
+        p.rows_per_rank = push->rows_per_rank;
+        p.task_rot = (int)(((int64_t)((push->src_rank + 1) % push->n_ranks) * push->rows_per_rank) / run);
+        for (int r = 0; r < push->n_ranks; ++r) {
+            p.peer_out[r] = static_cast<float*>(push->outs[r]);
+            p.peer_cnt[r] = static_cast<int32_t*>(push->cnts[r]);
+        }
+    }
     p.xyz = xyz; p.N = N; p.K4 = K4; p.w2c = w2c; p.v_begin = view_begin; p.v_end = view_end;
     p.depth = depth; p.depth_u16 = depth_dtype == SD3D_U16; p.Hd = Hd; p.Wd = Wd;
     p.fmap = fmap; p.Hf = Hf; p.Wf = Wf; p.C = C; p.stride = stride; p.inv_stride = pow2_reciprocal(stride); p.tau = tau; p.z_near = z_near;
-    p.accumulate = accumulate; p.finalize = finalize; p.by_pos = (variant & 1024) ? 1 : 0; p.order = order; p.out = out_feat; p.count = count;
+    p.accumulate = accumulate; p.finalize = finalize; p.by_pos = ((variant & 1024) || push != nullptr) ? 1 : 0; p.order = order; p.out = out_feat; p.count = count;
     p.pix_idx = pix_idx; p.vis = vis; p.pool = pool ? 1 : 0; p.seg_offsets = seg_offsets;
     p.task_offsets = task_offsets; p.task_seg = task_seg; p.S = (int32_t)S; p.run = run;
     p.partials = reinterpret_cast<float*>(ws);
@@ -1035,4 +1095,130 @@ extern "C" int sd3d_scale_mean(const float* const* feats_host, int L, int64_t nu
     const unsigned grid = (unsigned)imin64(ceil_div64(numel, 256), (int64_t)num_sms() * 16);
     scale_mean_kernel<<<grid, 256, 0, stream>>>(ptrs, L, numel, out);
     return check_launch("sd3d_scale_mean");
+}
+
+extern "C" int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin,
+                         int view_end, const void* depth, int depth_dtype, int Hd, int Wd, const void* fmap,
+                         int fmap_dtype, int Hf, int Wf, int C, float stride, float tau, float z_near, int accumulate,
+                         int finalize, const int32_t* order, float* out_feat, int32_t* count, int32_t* pix_idx,
+                         uint8_t* vis, const int32_t* seg_offsets, int64_t S, const int32_t* task_offsets,
+                         const int32_t* task_seg, int64_t max_tasks, int run, void* ws, size_t ws_bytes, int pool_,
+                         int variant, void* stream_) {
+    return lift_impl(xyz, N, K4, w2c, V, view_begin, view_end, depth, depth_dtype, Hd, Wd, fmap, fmap_dtype, Hf, Wf, C,
+                     stride, tau, z_near, accumulate, finalize, order, out_feat, count, pix_idx, vis, seg_offsets, S,
+                     task_offsets, task_seg, max_tasks, run, ws, ws_bytes, pool_, variant, stream_, nullptr);
+}
+
+extern "C" int sd3d_lift_push(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin,
+                              int view_end, const void* depth, int depth_dtype, int Hd, int Wd, const void* fmap,
+                              int fmap_dtype, int Hf, int Wf, int C, float stride, float tau, float z_near,
+                              const int32_t* order, int run, void* ws, size_t ws_bytes, int n_ranks, int src_rank,
+                              int64_t rows_per_rank, void* const* peer_sum, void* const* peer_count, int variant,
+                              void* stream_) {
+    PushTargets t;
+    t.n_ranks = n_ranks;
+    t.src_rank = src_rank;
+    t.rows_per_rank = rows_per_rank;
+    t.outs = peer_sum;
+    t.cnts = peer_count;
+    return lift_impl(xyz, N, K4, w2c, V, view_begin, view_end, depth, depth_dtype, Hd, Wd, fmap, fmap_dtype, Hf, Wf, C,
+                     stride, tau, z_near, 0, 0, order, nullptr, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr,
+                     0, run, ws, ws_bytes, 0, variant & ~2, stream_, &t);
+}
+
+namespace sd3d {
+// rows of this rank after all ranks have pushed: feat[l] = (sum over source ranks, ascending) / max(total count, 1)
+__global__ void __launch_bounds__(256) push_reduce_kernel(const float* __restrict__ stage_sum,
+                                                          const int32_t* __restrict__ stage_cnt, int n_ranks,
+                                                          int64_t rows_per_rank, int64_t rows, int C,
+                                                          float* __restrict__ feat, int32_t* __restrict__ count) {
+    const int vec_per_row = C >> 2;
+    const int64_t total = rows * vec_per_row;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = e / vec_per_row;
+        const int cv = (int)(e - l * vec_per_row);
+        int32_t cnt = 0;
+        float4 acc = f4_zero();
+        for (int r = 0; r < n_ranks; ++r) {
+            const int64_t slot = (int64_t)r * rows_per_rank + l;
+            cnt += stage_cnt[slot];
+            acc = f4_add(acc, *reinterpret_cast<const float4*>(stage_sum + slot * C + 4 * cv));
+        }
+        *reinterpret_cast<float4*>(feat + l * C + 4 * cv) = f4_div(acc, (float)max(cnt, 1));
+        if (cv == 0) count[l] = cnt;
+    }
+}
+}  // namespace sd3d
+
+extern "C" int sd3d_push_reduce(const float* stage_sum, const int32_t* stage_count, int n_ranks, int64_t rows_per_rank,
+                                int64_t rows, int C, float* feat, int32_t* count, void* stream_) {
+    if (n_ranks < 1 || rows_per_rank < rows || rows < 0 || C <= 0 || C % 4 != 0) {
+        set_error("sd3d_push_reduce: bad shape ranks=%d rows_per_rank=%lld rows=%lld C=%d", n_ranks,
+                  (long long)rows_per_rank, (long long)rows, C);
+        return SD3D_ERR_ARG;
+    }
+    if (rows == 0) return SD3D_OK;
+    if (stage_sum == nullptr || stage_count == nullptr || feat == nullptr || count == nullptr || !aligned16(stage_sum) ||
+        !aligned16(feat)) {
+        set_error("sd3d_push_reduce: null or misaligned buffer");
+        return SD3D_ERR_ARG;
+    }
+    const int64_t total = rows * (C / 4);
+    const unsigned grid = (unsigned)imin64(ceil_div64(total, 256), (int64_t)num_sms() * 8);
+    push_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(stage_sum, stage_count, n_ranks, rows_per_rank, rows, C,
+                                                                feat, count);
+    return check_launch("sd3d_push_reduce");
+}
+
+// ---- peer-mapped staging memory (one process per GPU: CUDA IPC) ----
+extern "C" int sd3d_peer_alloc(size_t bytes, void** ptr) {
+    if (ptr == nullptr || bytes == 0) {
+        set_error("sd3d_peer_alloc: bad argument");
+        return SD3D_ERR_ARG;
+    }
+    const cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess) {
+        set_error("sd3d_peer_alloc: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+        return SD3D_ERR_CUDA;
+    }
+    return SD3D_OK;
+}
+extern "C" int sd3d_peer_free(void* ptr) {
+    if (ptr != nullptr && cudaFree(ptr) != cudaSuccess) {
+        set_error("sd3d_peer_free: %s", cudaGetErrorString(cudaGetLastError()));
+        return SD3D_ERR_CUDA;
+    }
+    return SD3D_OK;
+}
+extern "C" int sd3d_ipc_export(void* ptr, uint8_t* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    if (ptr == nullptr || handle64 == nullptr || cudaIpcGetMemHandle(&h, ptr) != cudaSuccess) {
+        set_error("sd3d_ipc_export: %s", cudaGetErrorString(cudaGetLastError()));
+        return SD3D_ERR_CUDA;
+    }
+    memcpy(handle64, &h, 64);
+    return SD3D_OK;
+}
+extern "C" int sd3d_ipc_import(const uint8_t* handle64, void** ptr) {
+    cudaIpcMemHandle_t h;
+    if (handle64 == nullptr || ptr == nullptr) {
+        set_error("sd3d_ipc_import: null argument");
+        return SD3D_ERR_ARG;
+    }
+    memcpy(&h, handle64, 64);
+    const cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        set_error("sd3d_ipc_import: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return SD3D_ERR_CUDA;
+    }
+    return SD3D_OK;
+}
+extern "C" int sd3d_ipc_close(void* ptr) {
+    if (ptr != nullptr && cudaIpcCloseMemHandle(ptr) != cudaSuccess) {
+        set_error("sd3d_ipc_close: %s", cudaGetErrorString(cudaGetLastError()));
+        return SD3D_ERR_CUDA;
+    }
+    return SD3D_OK;
 }

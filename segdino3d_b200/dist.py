@@ -131,159 +131,105 @@ def lift_view_sharded(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: torch
     return out
 
 
-def lift_view_sharded_overlapped(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: torch.Tensor,
-                                 depth_local: torch.Tensor, fmap_local: torch.Tensor, sp_ids: torch.Tensor,
-                                 n_superpoints: int, *, stride: Optional[float] = None, tau: float = 0.05,
-                                 z_near: float = 0.1, n_chunks: int = 4, variant: int = 0, group=None):
-    """View-sharded lifting with the NVLink exchange OVERLAPPED with the gather (CUDA + NCCL only).
+class PeerStage:
+    """Staging buffers of the fused gather + exchange (``exchange="p2p"``): on every rank, ``n_buffers`` regions
+    of [world][rows_per_rank][C] f32 partial sums + [world][rows_per_rank] i32 counts in plain cudaMalloc memory,
+    mapped into every other rank's address space with CUDA IPC (handles exchanged once with an all_gather).
+    One process per GPU; all ranks must construct it collectively with the same arguments."""
 
-    The partial sums are written in *processing-position* order, laid out chunk-major so that chunk k is one
-    contiguous block holding, for every rank r, the k-th slice of r's position shard:
+    def __init__(self, rows_per_rank: int, channels: int, device: torch.device, group=None, n_buffers: int = 2):
+        import ctypes
+        from . import _lib
+        self.lib = _lib.load()
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.rows, self.c, self.device, self.n_buffers = int(rows_per_rank), int(channels), device, n_buffers
+        sum_bytes = (self.world * self.rows * self.c * 4 + 255) // 256 * 256
+        cnt_bytes = (self.world * self.rows * 4 + 255) // 256 * 256
+        self._own, self._imported = [], []
+        self.sum_ptrs, self.cnt_ptrs = [], []   # [buffer][rank] device addresses valid on this device
+        with torch.cuda.device(device):
+            for _ in range(n_buffers):
+                base = ctypes.c_void_p()
+                _lib.check(self.lib.sd3d_peer_alloc(sum_bytes + cnt_bytes, ctypes.byref(base)), "sd3d_peer_alloc")
+                self._own.append(base.value)
+                handle = (ctypes.c_uint8 * 64)()
+                _lib.check(self.lib.sd3d_ipc_export(base, handle), "sd3d_ipc_export")
+                mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+                every = torch.empty(self.world * 64, dtype=torch.uint8, device=device)
+                dist.all_gather_into_tensor(every, mine, group=group)
+                every = every.cpu().view(self.world, 64)
+                bases = []
+                for r in range(self.world):
+                    if r == self.rank:
+                        bases.append(base.value)
+                        continue
+                    h = (ctypes.c_uint8 * 64)(*every[r].tolist())
+                    peer = ctypes.c_void_p()
+                    _lib.check(self.lib.sd3d_ipc_import(h, ctypes.byref(peer)), "sd3d_ipc_import")
+                    self._imported.append(peer.value)
+                    bases.append(peer.value)
+                self.sum_ptrs.append(bases)
+                self.cnt_ptrs.append([b + sum_bytes for b in bases])
 
-        buffer row j = k*(R*B) + r*B + b   <->   position r*(n_chunks*B) + k*B + b   <->   point order[position]
+    def close(self) -> None:
+        import ctypes
+        torch.cuda.synchronize(self.device)
+        for ptr in self._imported:
+            self.lib.sd3d_ipc_close(ctypes.c_void_p(ptr))
+        self._imported = []
+        if dist.is_initialized():
+            dist.barrier()  # nobody still maps our memory
+        for ptr in self._own:
+            self.lib.sd3d_peer_free(ctypes.c_void_p(ptr))
+        self._own = []
 
-    Chunk k is gathered by one launch of the gather kernel (same kernel, `order`/`out` pointers offset, rows
-    indexed by position); as soon as it is done a reduce_scatter of that block runs on a second stream while
-    chunk k+1 is being gathered. Rank r ends up with the reduced rows of the CONTIGUOUS position shard
-    [r*n_chunks*B, (r+1)*n_chunks*B), finalises them, pools the superpoint pieces inside its shard and an
-    all-reduce of the small [S,C] sums (+ sizes) finishes the pooling.
 
-    Returns a dict: ``feat_shard`` (rows = positions ``rows[0]..rows[1]`` of ``order``), ``order`` (int32 [N]:
-    position -> point id), ``count`` (int32 [N] by POINT id), ``sp_feat`` [S,C] (same on every rank)."""
-    from . import _lib, ops as _ops
-    from .ops import _ptr, _stream, _DEPTH_CODE, _FMAP_CODE, SuperpointPlan
-    lib = _lib.load()
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    dev = xyz.device
+def lift_view_sharded_p2p(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: torch.Tensor, depth_local: torch.Tensor,
+                          fmap_local: torch.Tensor, sp_ids: torch.Tensor, n_superpoints: int, stage: PeerStage, *,
+                          stride: Optional[float] = None, tau: float = 0.05, z_near: float = 0.1, step: int = 0,
+                          variant: int = 0, group=None):
+    """View-sharded lifting with the exchange FUSED into the gather kernel (CUDA + NVLink peer memory).
+
+    Every rank lifts its own views for all points; the gather kernel stores each finished partial row straight into
+    the staging buffer of the rank that owns the row's processing position (peer store over NVLink, overlapped with
+    the rest of the gather). A one-element all_reduce is the only barrier; then each rank sums its staged rows in
+    rank order, divides by the global count and pools its position shard. No collective moves feature rows.
+
+    Returns ``feat_shard`` [rows,C] for processing positions ``rows=(begin,end)`` (point ids ``pids``),
+    ``count_shard`` [rows] and ``sp_feat`` [S,C] (identical on all ranks). ``step`` selects the staging buffer
+    (consecutive scenes must alternate)."""
+    from . import ops
+    world, rank = stage.world, stage.rank
     n, c = xyz.shape[0], fmap_local.shape[3]
-    v = K_local.shape[0]
-    hd, wd = depth_local.shape[1], depth_local.shape[2]
-    hf, wf = fmap_local.shape[1], fmap_local.shape[2]
-    stride = float(wd / wf if stride is None else stride)
-    xyz, K_local, w2c_local, depth_local, fmap_local = (t.contiguous() for t in (xyz, K_local, w2c_local, depth_local, fmap_local))
-    s = int(n_superpoints)
-    blk = (n + world * n_chunks - 1) // (world * n_chunks)
-    blk = (blk + 31) // 32 * 32                       # B: rows per (chunk, rank) block
-    shard_rows = n_chunks * blk                       # positions owned by one rank
-    n_pad = world * shard_rows
-    sum_j = torch.empty(n_pad, c, dtype=torch.float32, device=dev)
-    cnt_j = torch.empty(n_pad, dtype=torch.int32, device=dev)
-    shard = torch.empty(shard_rows, c, dtype=torch.float32, device=dev)
-    ws_bytes = int(lib.sd3d_lift_workspace_bytes(n, v, c, 0))
-    ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
-    def call(stage_bits, n_sub, order_t, out_t, cnt_t):
-        _lib.check(lib.sd3d_lift(_ptr(xyz), n_sub, _ptr(K_local), _ptr(w2c_local), v, 0, v, _ptr(depth_local),
-                                 _DEPTH_CODE[depth_local.dtype], hd, wd, _ptr(fmap_local), _FMAP_CODE[fmap_local.dtype],
-                                 hf, wf, c, stride, float(tau), float(z_near), 0, 0, _ptr(order_t), _ptr(out_t),
-                                 _ptr(cnt_t), None, None, None, 0, None, None, 0, _ops.DEFAULT_RUN, _ptr(ws), ws_bytes, 0,
-                                 int(variant) | stage_bits, _stream()), "sd3d_lift")
-
-    compute = torch.cuda.current_stream(dev)
-    comm = _comm_stream(dev)
-    with torch.cuda.device(dev):
-        # projection of every point against the local views on the side stream, concurrently with the plan
-        fork, join = torch.cuda.Event(), torch.cuda.Event()
-        fork.record(compute)
-        with torch.cuda.stream(comm):
-            comm.wait_event(fork)
-            call(256, n, None, sum_j, cnt_j)
-            join.record(comm)
-        plan = _ops.sp_sort(sp_ids, s, xyz=xyz)
-        # "positions" follow the run table: superpoints along the world Morton curve (L2 locality of the gather),
-        # refined order inside each superpoint; superpoints stay contiguous
-        seg_first_task = plan.task_offsets[: s + 1].long()
-        seg_order = torch.argsort(seg_first_task)                      # segments (incl. the invalid-id one) by task rank
-        old_off = plan.seg_offsets.long()
-        sizes_all = (old_off[1: s + 2] - old_off[: s + 1])
-        new_sizes = sizes_all[seg_order]
-        new_off_sorted = torch.cumsum(new_sizes, 0) - new_sizes        # start of every segment in the new sequence
-        seg_of_pos = torch.repeat_interleave(torch.arange(s + 1, device=dev), new_sizes, output_size=n)
-        old_pos = old_off[seg_order][seg_of_pos] + (torch.arange(n, device=dev) - new_off_sorted[seg_of_pos])
-        order_t = plan.order[old_pos]                                  # int32 [N]: position -> point id
-        seg_off_t = torch.empty(s + 1, dtype=torch.long, device=dev)   # start of superpoint id s in the new sequence
-        seg_off_t[seg_order] = new_off_sorted
-        seg_size_t = sizes_all
-        pos_of_j = _pos_of_j(n_pad, world, n_chunks, blk, dev)
-        order_pad = torch.cat([order_t, order_t.new_zeros(n_pad - n)]) if n_pad > n else order_t
-        order_j = order_pad[pos_of_j].contiguous()    # padding rows lift point order[0] again and are discarded
-        compute.wait_event(join)
-        works = []
-        chunk_rows = world * blk
-        for k in range(n_chunks):
-            lo = k * chunk_rows
-            call(512 | 1024, chunk_rows, order_j[lo:], sum_j[lo:], cnt_j[lo:])
-            if world > 1:
-                ev = torch.cuda.Event()
-                ev.record(compute)
-                with torch.cuda.stream(comm):
-                    comm.wait_event(ev)
-                    works.append(dist.reduce_scatter_tensor(shard[k * blk:(k + 1) * blk], sum_j[lo:lo + chunk_rows],
-                                                            op=dist.ReduceOp.SUM, group=group, async_op=True))
-            else:
-                shard[k * blk:(k + 1) * blk].copy_(sum_j[lo:lo + chunk_rows])
-        if world > 1:
-            with torch.cuda.stream(comm):
-                works.append(dist.all_reduce(cnt_j, op=dist.ReduceOp.SUM, group=group, async_op=True))
-            for w in works:
-                w.wait()                               # the compute stream waits for the exchange
-        # this rank's contiguous position shard
-        b = rank * shard_rows
-        e = min(b + shard_rows, n)
-        valid = max(e - b, 0)
-        cnt_shard = cnt_j.view(n_chunks, world, blk)[:, rank, :].reshape(-1)[:valid].contiguous()
-        feat_shard = _ops.lift_finalize(shard[:valid], cnt_shard) if valid > 0 else shard[:0]
-        # superpoint pieces inside the shard: clip every superpoint's [start, end) to [b, e). The pieces are not
-        # in id order, so the pooling kernel gets them through an explicit (piece start, piece end) table:
-        # perm = shard rows listed superpoint by superpoint, offsets = running piece sizes
-        st = seg_off_t.clamp(min=b, max=max(e, b)) - b                         # [S+1] incl. the invalid-id segment
-        en = (seg_off_t + seg_size_t).clamp(min=b, max=max(e, b)) - b
-        piece = en - st                                                        # sums to `valid` exactly
-        off_local = torch.zeros(s + 2, dtype=torch.long, device=dev)
-        off_local[1:] = torch.cumsum(piece, 0)
-        seg_of_row = torch.repeat_interleave(torch.arange(s + 1, device=dev), piece, output_size=int(valid))
-        rows_by_seg = (st[seg_of_row] + (torch.arange(valid, device=dev) - off_local[: s + 1][seg_of_row])).to(torch.int32)
-        off32 = off_local.to(torch.int32).contiguous()
-        local_plan = SuperpointPlan(rows_by_seg.contiguous(), rows_by_seg, off32, off32, off32, valid, s, _ops.DEFAULT_RUN, 0)
-        sizes = piece[:s].to(torch.float32)
-        sp_sum = _ops.sp_mean(feat_shard.contiguous(), local_plan, exact=True) * sizes[:, None]
-        if world > 1:
-            dist.all_reduce(sp_sum, op=dist.ReduceOp.SUM, group=group)
-            dist.all_reduce(sizes, op=dist.ReduceOp.SUM, group=group)
-        sp_feat = sp_sum / sizes.clamp(min=1)[:, None]
-        # global counts by point id
-        cnt_pos = cnt_j.view(n_chunks, world, blk).permute(1, 0, 2).reshape(-1)[:n]
-        count = torch.empty(n, dtype=torch.int32, device=dev)
-        count[order_t.long()] = cnt_pos
-    return {"feat_shard": feat_shard, "rows": (b, e), "order": order_t, "count": count, "sp_feat": sp_feat}
+    if stage.rows * world < n or stage.c != c:
+        raise ValueError("PeerStage is too small for this scene")
+    b = step % stage.n_buffers
+    # plan first: the projection kernel is several times faster on the plan's spatially sorted order (neighbouring
+    # lanes read neighbouring depth pixels) than it gains from running concurrently with the plan (measured, cfg4s)
+    plan = ops.sp_sort(sp_ids, n_superpoints, xyz=xyz)
+    ops.lift_push(xyz, K_local, w2c_local, depth_local, fmap_local, stride, plan, n_ranks=world, src_rank=rank,
+                  rows_per_rank=stage.rows, peer_sum=stage.sum_ptrs[b], peer_count=stage.cnt_ptrs[b], tau=tau,
+                  z_near=z_near, variant=variant)
+    token = torch.zeros(1, device=xyz.device)
+    dist.all_reduce(token, group=group)  # barrier on the stream: every rank's gather (and its peer stores) is complete
+    begin = min(rank * stage.rows, n)
+    end = min(begin + stage.rows, n)
+    feat_shard, cnt_shard = ops.push_reduce(stage.sum_ptrs[b][rank], stage.cnt_ptrs[b][rank], world, stage.rows,
+                                            end - begin, c, xyz.device)
+    # positions are superpoint-sorted: pool the local rows, turn means back into sums, reduce the tiny [S,C]
+    pids = plan.order[begin:end]
+    local_ids = sp_ids[pids.long()].contiguous()
+    local_plan = ops.sp_sort(local_ids, n_superpoints)
+    s = n_superpoints
+    sizes = (local_plan.seg_offsets[1:s + 1] - local_plan.seg_offsets[:s]).to(torch.float32)
+    sp_sum = ops.sp_mean(feat_shard, local_plan, exact=False) * sizes[:, None]
+    dist.all_reduce(sp_sum, group=group)
+    dist.all_reduce(sizes, group=group)
+    return {"feat_shard": feat_shard, "count_shard": cnt_shard, "rows": (begin, end), "pids": pids,
+            "sp_feat": sp_sum / sizes.clamp(min=1)[:, None]}
 
 
-_COMM_STREAMS = {}
-_POS_CACHE = {}
-
-
-def _pos_of_j(n_pad: int, world: int, n_chunks: int, blk: int, dev: torch.device) -> torch.Tensor:
-    """buffer row j -> position (static for a given geometry; cached)."""
-    key = (n_pad, world, n_chunks, blk, dev.index)
-    t = _POS_CACHE.get(key)
-    if t is None:
-        if len(_POS_CACHE) > 8:
-            _POS_CACHE.clear()
-        t = torch.arange(n_pad, device=dev).view(world, n_chunks, blk).permute(1, 0, 2).reshape(-1).contiguous()
-        _POS_CACHE[key] = t
-    return t
-
-
-def _comm_stream(dev: torch.device) -> torch.cuda.Stream:
-    st = _COMM_STREAMS.get(dev.index)
-    if st is None:
-        st = _COMM_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
-    return st
-
-
-# ------------------------------------------------------------------------------------------------------
-# bench leg (bench.py --mode viewshard): one large scene, strong scaling over ranks
-# ------------------------------------------------------------------------------------------------------
 def bench_viewshard(args, rank: int, world: int, dev: torch.device):
     from bench import WORKLOADS, ClockSampler, algorithmic_bytes, measured_peak_hbm
     from .synth import make_scene
@@ -299,11 +245,20 @@ def bench_viewshard(args, rank: int, world: int, dev: torch.device):
     del sc.fmap
     torch.cuda.empty_cache()
     ops = cuda_ops(variant=args.variant)
+    stage = None
+    if args.exchange == "p2p" and world > 1:
+        rows = (wl["n_points"] + world - 1) // world
+        stage = PeerStage(rows, wl["channels"], dev)
+    step_no = [0]
 
     def step():
-        if args.exchange == "overlap":
-            return lift_view_sharded_overlapped(d["xyz"], K_l, w2c_l, depth_l, fmap_l, d["sp_ids"], sc.n_superpoints,
-                                                stride=sc.stride, n_chunks=args.chunks, variant=args.variant)
+        if stage is not None:
+            step_no[0] += 1
+            return lift_view_sharded_p2p(d["xyz"], K_l, w2c_l, depth_l, fmap_l, d["sp_ids"], sc.n_superpoints, stage,
+                                         stride=sc.stride, step=step_no[0], variant=args.variant)
+        if args.exchange == "p2p":  # one rank: nothing to exchange
+            return lift_view_sharded(d["xyz"], K_l, w2c_l, depth_l, fmap_l, d["sp_ids"], sc.n_superpoints,
+                                     stride=sc.stride, exchange="allreduce", ops=ops)
         return lift_view_sharded(d["xyz"], K_l, w2c_l, depth_l, fmap_l, d["sp_ids"], sc.n_superpoints,
                                  stride=sc.stride, exchange=args.exchange, ops=ops)
 
@@ -350,5 +305,7 @@ def bench_viewshard(args, rank: int, world: int, dev: torch.device):
             "clocks": clocks, "gpu_launches": (6 + 2) * args.steps,
         }
         print(json.dumps(line), flush=True)
+    if stage is not None:
+        stage.close()
     if world > 1:
         dist.destroy_process_group()

@@ -36,15 +36,22 @@ def _worker(rank, world, port, exchange, out_dir):
         args = (sc.xyz.to(dev), sc.K[vb:ve].contiguous().to(dev), sc.w2c[vb:ve].contiguous().to(dev),
                 sc.depth[vb:ve].contiguous().to(dev), sc.fmap[vb:ve].contiguous().to(dev), sc.sp_ids.to(dev),
                 sc.n_superpoints)
-        if exchange == "overlap":
-            from segdino3d_b200.dist import lift_view_sharded_overlapped
-            r = lift_view_sharded_overlapped(*args, stride=sc.stride, n_chunks=3)
-            # rebuild the full point-id-ordered feature matrix from the position shards of all ranks
-            full = torch.zeros(sc.xyz.shape[0], r["feat_shard"].shape[1], device=dev)
-            b, e = r["rows"]
-            full[r["order"][b:e].long()] = r["feat_shard"]
-            dist.all_reduce(full)
-            r = {"feat": full, "count": r["count"], "sp_feat": r["sp_feat"]}
+        if exchange == "p2p":
+            from segdino3d_b200.dist import PeerStage, lift_view_sharded_p2p
+            n = sc.xyz.shape[0]
+            stage = PeerStage((n + world - 1) // world, 256, dev)
+            full = cnt = None
+            for step in range(3):  # consecutive scenes alternate the staging buffers
+                r = lift_view_sharded_p2p(*args, stage, stride=sc.stride, step=step)
+                full = torch.zeros(n, r["feat_shard"].shape[1], device=dev)
+                cnt = torch.zeros(n, dtype=torch.int32, device=dev)
+                full[r["pids"].long()] = r["feat_shard"]
+                cnt[r["pids"].long()] = r["count_shard"]
+                dist.all_reduce(full)
+                dist.all_reduce(cnt)
+            r = {"feat": full, "count": cnt, "sp_feat": r["sp_feat"]}
+            torch.cuda.synchronize()
+            stage.close()
         else:
             r = lift_view_sharded(*args, stride=sc.stride, exchange=exchange, gather_feats=True)
         torch.cuda.synchronize()
@@ -54,7 +61,7 @@ def _worker(rank, world, port, exchange, out_dir):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("exchange", ["allreduce", "reduce_scatter", "overlap"])
+@pytest.mark.parametrize("exchange", ["allreduce", "reduce_scatter", "p2p"])
 def test_view_sharded_nccl_matches_oracle(tmp_path, exchange):
     from oracle import lift_oracle as lo
     from oracle import scatter_oracle as so
