@@ -256,12 +256,22 @@ def run_ours(args):
     streams = [torch.cuda.Stream() for _ in range(max(args.streams, 1))]
     main_stream = torch.cuda.current_stream()
 
+    graphs = {}  # --graph: one captured CUDA graph per (scene, stream) slot, replayed instead of re-launching
+
     def run_steps(k, events_list=None):
         for st in streams:
             st.wait_stream(main_stream)
         for i in range(k):
             with torch.cuda.stream(streams[i % len(streams)]):
-                step(scenes[i % n_rot], None if events_list is None else events_list[i])
+                g = graphs.get((i % n_rot, i % len(streams)))
+                if g is not None and events_list is not None:
+                    events_list[i][0].record()
+                    g.replay()
+                    events_list[i][1].record()  # brackets the whole step in graph mode, not the gather alone
+                elif g is not None:
+                    g.replay()
+                else:
+                    step(scenes[i % n_rot], None if events_list is None else events_list[i])
         for st in streams:
             main_stream.wait_stream(st)
 
@@ -274,6 +284,17 @@ def run_ours(args):
     l1_bytes = pairs * 4 * c * 4
     run_steps(max(args.warmup, 3))
     torch.cuda.synchronize()
+    if args.graph:
+        import math
+        for slot in range(n_rot * len(streams) // math.gcd(n_rot, len(streams))):
+            key = (slot % n_rot, slot % len(streams))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=streams[key[1]]):
+                step(scenes[key[0]])
+            graphs[key] = g
+        torch.cuda.synchronize()
+        run_steps(max(args.warmup, 3))
+        torch.cuda.synchronize()
 
     lift_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                    for _ in range(args.steps)]
@@ -358,7 +379,7 @@ def run_ours(args):
                        "parallelism": "scene replicas (no collective)" if world > 1 else "single GPU",
                        "l2": f"inputs rotate over {n_rot} distinct scenes ({n_rot * 248} MB > 126 MB L2), no flush",
                        "run": args.run, "variant": args.variant, "streams": len(streams),
-                       "projection_overlaps_plan": not args.no_overlap},
+                       "projection_overlaps_plan": not args.no_overlap, "cuda_graph": bool(args.graph)},
             "points_per_s": value * n, "host_us_per_step": host_us,
             "roofline": {"bound": "hbm", "kernel": "gather_kernel (bilinear gather + view mean + run partials)",
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
@@ -420,6 +441,9 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="points-per-warp group (0=default, 1/2/4/8)")
     ap.add_argument("--no-refine", action="store_true", help="skip the Morton refinement of the processing order")
     ap.add_argument("--streams", type=int, default=2, help="scenes kept in flight on separate CUDA streams")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture each scene's step in a CUDA graph and replay it (launch-side cost ~0; in this mode "
+                         "roofline.kernel_ms brackets the whole step, use kernel_ms_alone for the gather)")
     ap.add_argument("--no-overlap", action="store_true", help="projection kernel on the main stream (no side stream)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -135,6 +135,7 @@ int sd3d_sp_combine(const void* partials, const int32_t* task_offsets, const int
  * its visible count straight into the staging buffers of the rank that owns the position:
  *     owner = i / rows_per_rank,  slot = src_rank * rows_per_rank + (i % rows_per_rank)
  *     peer_sum[owner][slot, :] = sum over this rank's visible views,  peer_count[owner][slot] = their number
+ * (the row is only sent when that number is > 0; sd3d_push_reduce ignores the rows of slots whose count is 0)
  * peer_sum[r] / peer_count[r] are device pointers valid on THIS device for rank r's staging buffers
  * ([n_ranks][rows_per_rank][C] f32 and [n_ranks][rows_per_rank] i32; peer-mapped with sd3d_ipc_import below, the
  * rank's own buffer directly). Stores to other ranks travel over NVLink while the kernel keeps gathering; no

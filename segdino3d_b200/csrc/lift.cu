@@ -538,17 +538,20 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const __grid
         }
         float* out_row = p.out + orow * p.C;
         int32_t* cnt_dst = p.count + orow;
+        bool store_row = true;
         if (p.n_peers > 0) {  // push mode: store straight into the owner rank's staging slot (NVLink peer store)
             const int owner = (int)(i / p.rows_per_rank);
             const int64_t slot = (int64_t)p.src_rank * p.rows_per_rank + (i - (int64_t)owner * p.rows_per_rank);
             out_row = p.peer_out[owner] + slot * p.C;
             cnt_dst = p.peer_cnt[owner] + slot;
+            store_row = cnt > 0;  // a point none of this rank's views sees sends its count (0) only: the reducer
+                                  // skips the slot, and a contiguous view shard sees a fraction of the scene
         }
         const float denom = (float)max(cnt, 1);
 #pragma unroll
         for (int k = 0; k < NV; ++k) {
             const int c = chan_of<FT>(k, lane);
-            if (c < p.C) {
+            if (c < p.C && store_row) {
                 const float4 o = p.finalize ? f4_div(acc[k], denom) : acc[k];
                 st_cs_f4(out_row + c, o);
                 sp_acc[k] = f4_add(sp_acc[k], o);
@@ -1141,8 +1144,10 @@ __global__ void __launch_bounds__(256) push_reduce_kernel(const float* __restric
         float4 acc = f4_zero();
         for (int r = 0; r < n_ranks; ++r) {
             const int64_t slot = (int64_t)r * rows_per_rank + l;
-            cnt += stage_cnt[slot];
-            acc = f4_add(acc, *reinterpret_cast<const float4*>(stage_sum + slot * C + 4 * cv));
+            const int32_t cr = stage_cnt[slot];
+            cnt += cr;
+            if (cr > 0)  // ranks that saw nothing of this point did not send a row (the slot holds stale data)
+                acc = f4_add(acc, *reinterpret_cast<const float4*>(stage_sum + slot * C + 4 * cv));
         }
         *reinterpret_cast<float4*>(feat + l * C + 4 * cv) = f4_div(acc, (float)max(cnt, 1));
         if (cv == 0) count[l] = cnt;
