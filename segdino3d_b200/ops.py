@@ -539,10 +539,52 @@ def lift_and_pool(xyz, K, pose_w2c, depth, fmap, sp_ids: torch.Tensor, n_superpo
 # ---------------------------------------------------------------------------------------------------
 # mask logits
 # ---------------------------------------------------------------------------------------------------
+def _mask_logits_raw(q: torch.Tensor, mf: torch.Tensor, code: int, threshold: Optional[float]):
+    """One ``sd3d_mask_logits`` call on contiguous float32 CUDA operands: out[n,S] (+ uint8 attention mask)."""
+    n, d = q.shape
+    s = mf.shape[0]
+    dev = q.device
+    with torch.cuda.device(dev):
+        out = torch.empty(n, s, dtype=torch.float32, device=dev)
+        attn = torch.empty(n, s, dtype=torch.uint8, device=dev) if threshold is not None else None
+        check(_lib.load().sd3d_mask_logits(_ptr(q), _ptr(mf), n, s, d, code, _ptr(out),
+                                           float(threshold) if threshold is not None else 0.0, _ptr(attn), _stream()),
+              "sd3d_mask_logits")
+    return out, attn
+
+
+class _MaskLogitsFn(torch.autograd.Function):
+    """Autograd for the mask-logit einsum (training calls it under autograd, engine/train_engine_3d.py:99-105):
+    with out = q @ mf^T,  grad_q = grad_out @ mf  and  grad_mf = grad_out^T @ q -- both are 'nd,md->nm' contractions
+    of transposed operands, so the backward reuses the same kernel (fp32 path: gradients stay at fp32 accuracy even
+    when the forward ran on the bf16 tensor-core path). The attention mask is not differentiable."""
+
+    @staticmethod
+    def forward(ctx, q, mf, code, threshold):
+        ctx.save_for_backward(q, mf)
+        out, attn = _mask_logits_raw(q, mf, code, threshold)
+        if attn is None:
+            return out
+        attn = attn.view(torch.bool)
+        ctx.mark_non_differentiable(attn)
+        return out, attn
+
+    @staticmethod
+    def backward(ctx, grad_out, *unused):
+        q, mf = ctx.saved_tensors
+        g = grad_out.contiguous()
+        grad_q = grad_mf = None
+        if ctx.needs_input_grad[0]:   # [n,S] x [d,S] -> [n,d]
+            grad_q, _ = _mask_logits_raw(g, mf.t().contiguous(), _lib.F32, None)
+        if ctx.needs_input_grad[1]:   # [S,n] x [d,n] -> [S,d]
+            grad_mf, _ = _mask_logits_raw(g.t().contiguous(), q.t().contiguous(), _lib.F32, None)
+        return grad_q, grad_mf, None, None
+
+
 def mask_logits(q: torch.Tensor, mf: torch.Tensor, precision: str = "fp32", threshold: Optional[float] = None):
     """``torch.einsum('nd,md->nm', q, mf)`` (instance_seg_3d_decoder.py:567). ``precision='bf16'`` runs the
     tcgen05 tensor-core kernel (bf16 operands, fp32 accumulate). With ``threshold`` also returns the fused
-    attention mask of :568-571 (bool [n,S])."""
+    attention mask of :568-571 (bool [n,S]). Differentiable in q and mf (``_MaskLogitsFn``)."""
     _need_cuda("q", q)
     _need_cuda("mf", mf)
     if q.dim() != 2 or mf.dim() != 2 or q.shape[1] != mf.shape[1]:
@@ -553,15 +595,9 @@ def mask_logits(q: torch.Tensor, mf: torch.Tensor, precision: str = "fp32", thre
     if code is None:
         raise ValueError("precision must be 'fp32' or 'bf16'")
     q, mf = q.contiguous(), mf.contiguous()
-    n, d = q.shape
-    s = mf.shape[0]
-    dev = q.device
-    with torch.cuda.device(dev):
-        out = torch.empty(n, s, dtype=torch.float32, device=dev)
-        attn = torch.empty(n, s, dtype=torch.uint8, device=dev) if threshold is not None else None
-        check(_lib.load().sd3d_mask_logits(_ptr(q), _ptr(mf), n, s, d, code, _ptr(out),
-                                           float(threshold) if threshold is not None else 0.0, _ptr(attn), _stream()),
-              "sd3d_mask_logits")
+    if torch.is_grad_enabled() and (q.requires_grad or mf.requires_grad):
+        return _MaskLogitsFn.apply(q, mf, code, threshold)
+    out, attn = _mask_logits_raw(q, mf, code, threshold)
     if threshold is not None:
         return out, attn.view(torch.bool)
     return out

@@ -561,3 +561,30 @@ def test_c_abi_error_codes():
     # and the library is still usable afterwards
     assert torch.equal(sd.scatter_mean(torch.ones(4, 4, device=DEV), torch.tensor([0, 0, 1, 1], device=DEV), dim=0).cpu(),
                        torch.ones(2, 4))
+
+
+
+@pytest.mark.parametrize("shape", [(200, 500, 256), (37, 129, 96)])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_mask_logits_backward_matches_einsum_autograd(shape, precision):
+    """grad_q = grad_out @ mf, grad_mf = grad_out^T @ q through the same kernel (fp32 path), against torch's einsum
+    autograd on the same device; the fused attention mask stays non-differentiable."""
+    n, s, d = shape
+    if precision == "bf16" and d % 64 != 0:
+        pytest.skip("tcgen05 path needs d % 64 == 0")
+    g = torch.Generator().manual_seed(n + s)
+    q0 = torch.randn(n, d, generator=g)
+    mf0 = torch.randn(s, d, generator=g) * 0.5
+    w = torch.randn(n, s, generator=g).to(DEV)
+    q, mf = q0.to(DEV).requires_grad_(True), mf0.to(DEV).requires_grad_(True)
+    out, attn = sd.mask_logits(q, mf, precision=precision, threshold=0.5)
+    assert attn.dtype == torch.bool and not attn.requires_grad
+    (out * w).sum().backward()
+    qr, mfr = q0.to(DEV).requires_grad_(True), mf0.to(DEV).requires_grad_(True)
+    (torch.einsum("nd,md->nm", qr, mfr) * w).sum().backward()
+    assert rel_row_err(q.grad, qr.grad, floor=1.0) <= 1e-5
+    assert rel_row_err(mf.grad, mfr.grad, floor=1.0) <= 1e-5
+    # only one operand requires grad
+    q2 = q0.to(DEV).requires_grad_(True)
+    sd.mask_logits(q2, mf0.to(DEV)).sum().backward()
+    assert rel_row_err(q2.grad, mf0.to(DEV).sum(0, keepdim=True).expand(n, d), floor=1.0) <= 1e-5
