@@ -95,3 +95,34 @@ def test_pth_wire_format_round_trip(tmp_path):
     assert torch.equal(fused, torch.stack([feats[0], feats[1].float()], 0).mean(0))
     with pytest.raises(ValueError):
         sd.save_points_2dfeats(str(tmp_path), "bad", [torch.zeros(3, 4), torch.zeros(4, 4)])
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    """SD3D_LIB points the loader at an experimental build; a path that does not exist must raise, never fall back."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setenv("SD3D_LIB", os.path.join(ROOT, "no_such_dir", "libsd3d.so"))
+    with pytest.raises(sd.Sd3dError, match="not found"):
+        _lib.load()
+    monkeypatch.delenv("SD3D_LIB")
+    assert _lib.load().sd3d_version() == 100
+
+
+def test_new_host_entries_reject_bad_arguments():
+    """the push / IPC entries validate before touching the device (no GPU needed for the error paths)."""
+    lib = _lib.load()
+    assert lib.sd3d_push_reduce(None, None, 0, 10, 5, 256, None, None, None) == _lib.ERR_ARG      # no ranks
+    assert lib.sd3d_push_reduce(None, None, 2, 4, 5, 256, None, None, None) == _lib.ERR_ARG       # rows > rows_per_rank
+    assert lib.sd3d_push_reduce(None, None, 2, 8, 0, 256, None, None, None) == _lib.OK            # nothing owned
+    assert lib.sd3d_peer_alloc(0, None) == _lib.ERR_ARG
+    assert lib.sd3d_ipc_import(None, None) == _lib.ERR_ARG
+    assert b"sd3d_ipc_import" in lib.sd3d_last_error()
+
+
+def test_bench_reads_ncu_traffic_from_profiles():
+    import argparse
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    traffic, src = bench.ncu_traffic(argparse.Namespace(workload="cfg2", variant=0, run=32))
+    assert src.startswith("profiles/") and 250e6 < traffic < 500e6
+    assert bench.ncu_traffic(argparse.Namespace(workload="cfg4", variant=0, run=32))[0] is None
