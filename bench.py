@@ -395,7 +395,7 @@ def run_ours(args):
                          "path_algorithmic_bytes": b_path,
                          "path_frac": b_path / (ms_per_step * 1e-3) / 1e9 / peak},
             "clocks": clocks,
-            "gpu_launches": (7 if args.no_refine else 8) * args.steps,
+            "gpu_launches": (5 if args.no_refine else 6) * args.steps,  # radix pass, run table, (refine,) projection, gather, combine
         }
         if e2e is not None:
             line["e2e"] = e2e

@@ -302,7 +302,9 @@ def bench_viewshard(args, rank: int, world: int, dev: torch.device):
             "roofline": {"bound": "hbm", "kernel": "whole path (lift + exchange + pool)", "achieved": b_path / (ms * 1e-3) / 1e9,
                          "peak": peak * world, "unit": "GB/s", "frac": b_path / (ms * 1e-3) / 1e9 / (peak * world),
                          "traffic": None, "peak_source": peak_src},
-            "clocks": clocks, "gpu_launches": (6 + 2) * args.steps,
+            "clocks": clocks,
+            # own kernels per scene: plan 3 + projection + gather + finalize / push-reduce + pooling (2-4)
+            "gpu_launches": (10 if world > 1 else 8) * args.steps,
         }
         print(json.dumps(line), flush=True)
     if stage is not None:
