@@ -588,3 +588,42 @@ def test_mask_logits_backward_matches_einsum_autograd(shape, precision):
     q2 = q0.to(DEV).requires_grad_(True)
     sd.mask_logits(q2, mf0.to(DEV)).sum().backward()
     assert rel_row_err(q2.grad, mf0.to(DEV).sum(0, keepdim=True).expand(n, d), floor=1.0) <= 1e-5
+
+
+def test_push_exchange_emulated_on_one_device():
+    """sd3d_lift_push + sd3d_push_reduce without a second GPU: (a) one rank owning everything is bit-identical to the
+    plain lift (rows in processing-position order); (b) two emulated ranks (view halves) pushing into two owners'
+    staging buffers on the same device: counts exact, features within 1e-5; staging starts as NaN / garbage so a row
+    that was not sent (count 0) must really be ignored."""
+    from segdino3d_b200 import ops
+    sc = make_scene(n_points=6001, n_views=11, hd=120, wd=160, stride=8, channels=256, seed=77, sp_target=40)
+    d = sc.to(DEV)
+    n, c = sc.xyz.shape[0], 256
+    plan = sd.sp_sort(d.sp_ids, sc.n_superpoints, xyz=d.xyz)
+    ref = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan)
+    order = plan.order.long()
+    ssum = torch.full((n, c), float("nan"), device=DEV)
+    scnt = torch.full((n,), -7, dtype=torch.int32, device=DEV)
+    ops.lift_push(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan, n_ranks=1, src_rank=0, rows_per_rank=n,
+                  peer_sum=[ssum.data_ptr()], peer_count=[scnt.data_ptr()])
+    feat, cnt = ops.push_reduce(ssum.data_ptr(), scnt.data_ptr(), 1, n, n, c, DEV)
+    assert torch.equal(cnt, ref["count"][order])
+    assert torch.equal(feat, ref["feat"][order])
+
+    ranks, rows = 2, (n + 1) // 2
+    stage_sum = [torch.full((ranks * rows, c), float("nan"), device=DEV) for _ in range(ranks)]
+    stage_cnt = [torch.full((ranks * rows,), -7, dtype=torch.int32, device=DEV) for _ in range(ranks)]
+    for r, (vb, ve) in enumerate([(0, 5), (5, 11)]):
+        ops.lift_push(d.xyz, d.K[vb:ve], d.w2c[vb:ve], d.depth[vb:ve], d.fmap[vb:ve], sc.stride, plan, n_ranks=ranks,
+                      src_rank=r, rows_per_rank=rows, peer_sum=[t.data_ptr() for t in stage_sum],
+                      peer_count=[t.data_ptr() for t in stage_cnt])
+    feats, cnts = [], []
+    for owner in range(ranks):
+        own = min(rows, n - owner * rows)
+        f, k = ops.push_reduce(stage_sum[owner].data_ptr(), stage_cnt[owner].data_ptr(), ranks, rows, own, c, DEV)
+        feats.append(f)
+        cnts.append(k)
+    assert torch.equal(torch.cat(cnts), ref["count"][order])
+    got = torch.cat(feats)
+    assert torch.isfinite(got).all()
+    assert rel_row_err(got, ref["feat"][order], floor=1.0) <= 1e-5
