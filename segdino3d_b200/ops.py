@@ -348,6 +348,19 @@ class _LiftLaunch:
         return {"feat": self.feat, "count": self.count, "pix_idx": self.pix, "vis": self.vis, "sp_feat": self.sp_out}
 
 
+def _timed_gather(L: "_LiftLaunch", plan, events) -> None:
+    """bench only. Two events bracket everything after the projection (stage planner + gather); three events
+    split it: events[0] | stage planner | events[1] | gather | events[2]."""
+    events[0].record()
+    if len(events) == 2:
+        L.call(512, plan)
+    else:
+        L.call(4096, plan)
+        events[1].record()
+        L.call(8192, plan)
+    events[-1].record()
+
+
 def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Tensor, fmap: torch.Tensor,
          stride: Optional[float] = None, *, tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT,
          views: Optional[Tuple[int, int]] = None, finalize: bool = True, plan: Optional[SuperpointPlan] = None,
@@ -371,9 +384,7 @@ def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Ten
         L.call(0, plan)
     else:  # bench only: bracket the gather kernel alone
         L.call(256, plan)
-        events[0].record()
-        L.call(512, plan)
-        events[1].record()
+        _timed_gather(L, plan, events)
     if pool:
         L.combine(plan)
     return L.result()
@@ -508,10 +519,9 @@ def lift_and_pool(xyz, K, pose_w2c, depth, fmap, sp_ids: torch.Tensor, n_superpo
         plan = sp_sort(sp_ids, n_superpoints, run=run, xyz=L.xyz)
         L.call(256, plan)
     if events is not None:
-        events[0].record()
-    L.call(512, plan)
-    if events is not None:
-        events[1].record()
+        _timed_gather(L, plan, events)
+    else:
+        L.call(512, plan)
     L.combine(plan)
     return L.feat, L.count, L.sp_out, plan
 

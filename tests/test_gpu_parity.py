@@ -244,6 +244,49 @@ def test_lift_kernel_variants_bit_exact(variant, run):
     assert rel_row_err(r["sp_feat"], sp_o, floor=0.1) <= 1e-5
 
 
+@pytest.mark.parametrize("variant", [0, 4, 8, 12, 2048])
+@pytest.mark.parametrize("cfg", [dict(n_points=6000, n_views=40, hd=120, wd=160, stride=8, channels=256, seed=23),
+                                 dict(n_points=9000, n_views=13, hd=60, wd=80, stride=4, channels=64, seed=24),
+                                 dict(n_points=5000, n_views=5, hd=96, wd=128, stride=2, channels=128, seed=25),
+                                 dict(n_points=4000, n_views=3, hd=60, wd=80, stride=4, channels=512, seed=26),
+                                 dict(n_points=700, n_views=70, hd=48, wd=64, stride=8, channels=8, seed=27)])
+def test_staged_gather_bit_exact(cfg, variant):
+    """With a plan (run = 32) the gather stages every distinct tap pixel of a (run, view) in shared memory with
+    bulk copies and blends from there (variant 0; bit 2 = two samples in flight, bit 3 = 8 consumer warps x 4
+    points); 2048 forces the direct gather. All of them: integers and fp32 sums bit-identical to the oracle,
+    border taps (small maps: many) read the zero row."""
+    sc = make_scene(sp_target=40, **cfg)
+    a, c, _, _ = lo.lift_accumulate_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride)
+    d = sc.to(DEV)
+    plan = sd.sp_sort(d.sp_ids, sc.n_superpoints, xyz=d.xyz)
+    raw = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan, finalize=False, variant=variant)
+    assert torch.equal(raw["count"].cpu(), c) and torch.equal(raw["feat"].cpu(), a)
+    r = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan, pool=True, variant=variant)
+    feat_o = lo.lift_finalize_oracle(a, c)
+    assert torch.equal(r["feat"].cpu(), feat_o) and torch.equal(r["count"].cpu(), c)
+    assert rel_row_err(r["sp_feat"], so.scatter_mean_oracle(feat_o, sc.sp_ids, dim=0), floor=0.1) <= 1e-5
+    # view ranges chain through the staged kernel too (accumulate_into continues the per-point view loop)
+    v = sc.K.shape[0]
+    if v >= 3:
+        part = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan, finalize=False, views=(0, v // 3),
+                       variant=variant)
+        full = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan, finalize=False, views=(v // 3, v),
+                       accumulate_into=(part["feat"], part["count"]), variant=variant)
+        assert torch.equal(full["feat"].cpu(), a) and torch.equal(full["count"].cpu(), c)
+
+
+@pytest.mark.parametrize("fmap_dtype", [torch.float16, torch.bfloat16])
+def test_staged_gather_16bit_maps(fmap_dtype):
+    sc = make_scene(n_points=8000, n_views=20, hd=120, wd=160, stride=8, channels=256, seed=31, sp_target=60,
+                    fmap_dtype=fmap_dtype)
+    a, c, _, _ = lo.lift_accumulate_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride)
+    d = sc.to(DEV)
+    plan = sd.sp_sort(d.sp_ids, sc.n_superpoints, xyz=d.xyz)
+    for variant in (0, 4, 8, 2048):
+        raw = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan, finalize=False, variant=variant)
+        assert torch.equal(raw["count"].cpu(), c) and torch.equal(raw["feat"].cpu(), a), variant
+
+
 def test_lift_fma_variant_within_tolerance():
     """variant bit 0 contracts the blend into FFMA: integers stay bit-exact, features within 1e-5."""
     sc = make_scene(n_points=5000, n_views=40, hd=120, wd=160, stride=8, channels=256, seed=21, sp_target=50)
