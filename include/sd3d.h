@@ -115,7 +115,13 @@ int sd3d_sp_mean(const float* src, const int32_t* perm, const int32_t* seg_offse
  *   previous projection-only call left in the same ws (per-kernel timing, stream overlap);
  *   bit 10 (1024) = rows of out_feat / count are indexed by processing position i (point order[i]) instead
  *   of by point id (what sd3d_lift_push does for its staging rows);
- *   bits 5/6 (32/64) = default gather compiled for 5 / 3 resident CTAs per SM (tuning points).
+ *   bits 5/6 (32/64) = default gather compiled for 5 / 3 resident CTAs per SM (tuning points);
+ *   bit 15 (32768) = shared-memory STAGED gather (needs order, run = 32, C * elemsize <= 2048 and a multiple of 16,
+ *   else the direct gather runs): every distinct tap pixel of a (run, view) is copied once into shared memory by
+ *   cp.async.bulk and blended from there; same bits as the direct gather. With it, the projection call (which then
+ *   needs `order`) also plans the stages; after a projection WITHOUT order, bit 9 (512) runs a stand-alone stage
+ *   planner before the gather; bit 12 (4096) = that planner only, bit 13 (8192) = gather only, stages planned.
+ *   Bits 2 / 3 then mean: two samples in flight per consumer warp / 4 consumer warps x 8 points instead of 8 x 4.
  * --------------------------------------------------------------------------------------------- */
 size_t sd3d_lift_workspace_bytes(int64_t N, int n_views, int C, int64_t max_tasks);
 int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin, int view_end,

@@ -698,23 +698,30 @@ static int lift_impl(const float* xyz, int64_t N, const float* K4, const float* 
     sp.cap_pix = sp.ring_slots = 0;
     sp.masks = masks;
     sp.nchunks = nchunks;
-    if (do_project && nchunks > 0)
-        project_kernel<<<(unsigned)ceil_div64(N, kProjThreads), kProjThreads, 0, stream>>>(p, masks, nchunks, sp.done,
-                                                                                           sp.n_done);
-    if (!do_gather && !do_stage_plan) return check_launch("sd3d_lift(project)");
-    int rc;
-    if ((variant & (2 | 2048)) == 0 && staged_supported(p, fmap_dtype, n_views)) {
-        // default gather: tap rows staged in shared memory by the bulk-copy engine (lift_staged.cu)
-        rc = dispatch_staged(p, sp, fmap_dtype, variant, do_stage_plan, do_gather, stream);
+    const bool staged = (variant & 32768) != 0 && (variant & 2) == 0 && staged_supported(p, fmap_dtype, n_views);
+    if (staged) {
+        // variant bit 15: tap rows staged in shared memory by the bulk-copy engine (lift_staged.cu); the projection
+        // kernel of that path also plans the stages
+        const int plan_mode = do_project ? 2 : (do_stage_plan ? 1 : 0);
+        const int rc = dispatch_staged(p, sp, fmap_dtype, variant, plan_mode, masks, do_gather, stream);
         if (rc != SD3D_OK) {
             set_error("sd3d_lift: no staged gather for C=%d dtype=%d", C, fmap_dtype);
             return rc;
         }
         return check_launch("sd3d_lift(staged)");
     }
+    if (do_project && nchunks > 0)
+        project_kernel<<<(unsigned)ceil_div64(N, kProjThreads), kProjThreads, 0, stream>>>(p, masks, nchunks, sp.done,
+                                                                                           sp.n_done);
+    int rc;
     if (!do_gather) return check_launch("sd3d_lift(project)");
     switch (fmap_dtype) {
-        case SD3D_F32: rc = dispatch_gather<float>(p, masks, nchunks, n_tasks, variant, stream); break;
+        case SD3D_F32:
+            if ((variant & 16384) && C % 8 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 31u) == 0)  // experiment: LDG.256
+                rc = dispatch_gather<F32x8>(p, masks, nchunks, n_tasks, variant, stream);
+            else
+                rc = dispatch_gather<float>(p, masks, nchunks, n_tasks, variant, stream);
+            break;
         case SD3D_F16: rc = dispatch_gather<__half>(p, masks, nchunks, n_tasks, variant, stream); break;
         case SD3D_BF16: rc = dispatch_gather<__nv_bfloat16>(p, masks, nchunks, n_tasks, variant, stream); break;
         default:

@@ -66,6 +66,20 @@ struct Tap<float> {
         dst[0] = __ldg(reinterpret_cast<const float4*>(p));
     }
 };
+// fp32 rows read with ONE 256-bit load per lane and tap (sm_100 LDG.256): 8 consecutive channels = two float4 registers
+struct F32x8 {
+    float v;
+};
+template <>
+struct Tap<F32x8> {
+    static constexpr int kElems = 8, kRegs = 2;
+    __device__ __forceinline__ static void load(float4* dst, const F32x8* p) {
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(dst[0].x), "=f"(dst[0].y), "=f"(dst[0].z), "=f"(dst[0].w), "=f"(dst[1].x), "=f"(dst[1].y),
+                       "=f"(dst[1].z), "=f"(dst[1].w)
+                     : "l"(p));
+    }
+};
 template <>
 struct Tap<__half> {
     static constexpr int kElems = 8, kRegs = 2;

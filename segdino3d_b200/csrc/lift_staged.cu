@@ -34,10 +34,15 @@
 
 namespace sd3d {
 
-constexpr int kStQ = 8;         // stage queue entries per CTA
+constexpr int kStQ = 8;  // stage queue entries per CTA
 constexpr uint32_t kStFirst = 1u, kStLast = 2u, kStExit = 4u;
-constexpr uint32_t kRecDirect = 0x80000000u;  // record word 1, bit 31: taps come from global memory
-constexpr uint32_t kRankZero = 0x7Fu;         // slot rank of a tap outside the map
+// Sample record after planning (16 bytes, in place of K1's record):
+//   staged: x = off00 | off01 << 16, y = off10 | off11 << 16: offsets of the four tap rows from the stage's first ring
+//           slot, in 16-byte units (0xFFFF = tap outside the map); z = ax; w = ay, sign bit set if any tap is outside
+//   direct: x = pixel index of tap (y0, x0), y = tap-valid flags, z = ax with the sign bit set, w = ay
+// (ax, ay are in [0, 1): their sign bits are free)
+constexpr uint32_t kSignBit = 0x80000000u;
+constexpr uint32_t kOffZero = 0xFFFFu;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
@@ -96,7 +101,224 @@ __device__ __forceinline__ void task_range(const LiftParams& p, int64_t task, in
 }
 
 // ---------------------------------------------------------------------------------------------------
-// stage planner: one warp per (run, chunk of 8 views), lane = point of the run
+// stage building (shared by the fused projection kernel and the stand-alone planner)
+// ---------------------------------------------------------------------------------------------------
+// Stage header, 16 words: [0] view  [1] lane mask  [2] box origin (x | y << 16, int16 each)  [3] distinct pixels
+// [4..11] pixel bitmap, row r of the box = bits [16 r, 16 r + 16)  [12..15] 16 bytes: pixels in the rows before row r
+//
+// One view of one run, lane = point. `cand`: the lane's point is visible in view v with tap origin (x0, y0), tap-valid
+// flags, fractional offsets ax / ay and pixel index pix of tap (y0, x0). Cuts the candidates into at most kStMaxSub
+// stages (greedy boxes: leftmost candidate, then the topmost candidate within `box` columns of it; the box shrinks
+// until its distinct pixels fit `cap_pix`), appends their headers at H and returns their number. Every candidate lane
+// gets its final sample record in `out_rec` (see the format above).
+__device__ __forceinline__ int build_view_stages(bool cand, int x0, int y0, uint32_t flags, int ax_bits, int ay_bits,
+                                                 int pix, int v, uint32_t* __restrict__ H, int cap_pix, uint32_t rowb16,
+                                                 int lane, int4& out_rec) {
+    int nst = 0;
+    for (int sub = 0; sub < kStMaxSub; ++sub) {
+        if (!__any_sync(kFull, cand)) break;
+        uint32_t bm[8];
+        int xmin = 0, ymin = 0, npix = 0, cx = 0, cy = 0;
+        bool sel = false, small = false;
+        for (int box = 16; box >= 2; box >>= 1) {
+            xmin = __reduce_min_sync(kFull, cand ? x0 : 0x3fffffff);
+            const bool fitx = cand && (x0 - xmin <= box - 2);
+            ymin = __reduce_min_sync(kFull, fitx ? y0 : 0x3fffffff);
+            sel = fitx && (y0 - ymin <= box - 2);
+            cx = x0 - xmin;
+            cy = y0 - ymin;  // 0..14 when sel
+            small = !__any_sync(kFull, sel && (cx > 6 || cy > 6));
+            const uint32_t top = sel ? (flags & 3u) << cx : 0u, bot = sel ? ((flags >> 2) & 3u) << cx : 0u;
+            if (small) {  // the box fits 8 x 8: 64-bit bitmap, two reductions
+                const unsigned long long c64 = ((unsigned long long)top << (8 * cy)) | ((unsigned long long)bot << (8 * cy + 8));
+                bm[0] = __reduce_or_sync(kFull, (uint32_t)c64);
+                bm[1] = __reduce_or_sync(kFull, (uint32_t)(c64 >> 32));
+                npix = __popc(bm[0]) + __popc(bm[1]);
+            } else {
+                npix = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    uint32_t c = 0u;
+                    if ((cy >> 1) == w) c |= top << ((cy & 1) * 16);
+                    if (((cy + 1) >> 1) == w) c |= bot << (((cy + 1) & 1) * 16);
+                    bm[w] = __reduce_or_sync(kFull, c);
+                    npix += __popc(bm[w]);
+                }
+            }
+            if (npix <= cap_pix) break;
+        }
+        // number of bitmap bits below bit (row, col) = shared-memory slot of that pixel inside the stage
+        auto rank_of = [&](int row, int col) -> uint32_t {
+            if (small) {
+                const int b = row * 8 + col;
+                const uint32_t lo_m = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+                const uint32_t hi_m = b >= 32 ? ((1u << (b - 32)) - 1u) : 0u;
+                return (uint32_t)(__popc(bm[0] & lo_m) + __popc(bm[1] & hi_m));
+            }
+            const int b = row * 16 + col;
+            int rk = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                if (w < (b >> 5)) rk += __popc(bm[w]);
+                if (w == (b >> 5)) rk += __popc(bm[w] & ((1u << (b & 31)) - 1u));
+            }
+            return (uint32_t)rk;
+        };
+        const bool direct = (sub == kStMaxSub - 1) && cand && !sel;  // the view's leftovers ride on its last stage
+        const bool member = sel || direct;
+        const uint32_t mask = __ballot_sync(kFull, member);
+        if (sel) {
+            uint32_t off[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                off[t] = (flags & (1u << t)) ? rank_of(cy + (t >> 1), cx + (t & 1)) * rowb16 : kOffZero;
+            out_rec = make_int4((int)(off[0] | (off[1] << 16)), (int)(off[2] | (off[3] << 16)), ax_bits,
+                                flags != 15u ? (ay_bits | (int)kSignBit) : ay_bits);
+        } else if (direct) {
+            out_rec = make_int4(pix, (int)flags, ax_bits | (int)kSignBit, ay_bits);
+        }
+        // header: lanes 0..11 write one word each, lanes 16..31 the 16 row-prefix bytes
+        uint32_t* __restrict__ Hs = H + nst * 16;
+        if (lane < 12) {
+            uint32_t wv = 0u;
+            if (lane == 0) wv = (uint32_t)v;
+            if (lane == 1) wv = mask;
+            if (lane == 2) wv = ((uint32_t)xmin & 0xffffu) | ((uint32_t)ymin << 16);
+            if (lane == 3) wv = (uint32_t)npix;
+            if (lane >= 4) {
+                const int w = lane - 4;
+                if (small) {  // rows 2w, 2w+1 of the 8 x 8 bitmap -> two 16-bit rows
+                    const uint32_t two = w < 4 ? ((w < 2 ? bm[0] : bm[1]) >> (16 * (w & 1))) & 0xffffu : 0u;
+                    wv = (two & 0xffu) | ((two >> 8) << 16);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (k == w) wv = bm[k];
+                }
+            }
+            Hs[lane] = wv;
+        } else if (lane >= 16) {
+            const int r = lane - 16;
+            reinterpret_cast<uint8_t*>(Hs + 12)[r] = (uint8_t)(r < (small ? 8 : 16) ? rank_of(r, 0) : (uint32_t)npix);
+        }
+        if (member) cand = false;
+        ++nst;
+    }
+    return nst;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1 + stage planner in one pass (the default when a plan exists): one warp per run, lane = point of the run.
+// Projection and depth test exactly as project_kernel (lift.cu: same operations in the same order -> the same
+// pix_idx / vis / count bits); the warp then cuts each view's visible samples into stages while their tap geometry is
+// still in registers, so the records are written once, in their final form, and the run's headers are appended in
+// view order by the warp that owns the run (no atomics, no second pass over the records).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPsWarps = 4;
+constexpr int kPsViews = 4;  // views per round: 4 independent depth reads in flight per lane
+
+__global__ void __launch_bounds__(kPsWarps * 32) project_stage_kernel(const LiftParams p, uint32_t* __restrict__ masks,
+                                                                      int nchunks, const StagedParams sp) {
+    const int lane = lane_id();
+    const int64_t task = (int64_t)blockIdx.x * kPsWarps + (threadIdx.x >> 5);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *sp.counter = 0;  // the gather's run dispenser
+    const int64_t n_tasks = p.pool ? (int64_t)p.task_offsets[p.S + 1] : sp.n_tasks;
+    if (task >= n_tasks) return;
+    int seg, npts;
+    int64_t start;
+    task_range(p, task, seg, start, npts);
+    const bool has = lane < npts;
+    const int64_t pid = has ? (int64_t)p.order[start + lane] : 0;
+    float px = 0.f, py = 0.f, pz = 0.f;
+    if (has) {
+        px = __ldg(p.xyz + 3 * pid);
+        py = __ldg(p.xyz + 3 * pid + 1);
+        pz = __ldg(p.xyz + 3 * pid + 2);
+    }
+    const int64_t depth_elems = (int64_t)p.Hd * p.Wd;
+    const float wd_f = (float)p.Wd, hd_f = (float)p.Hd;
+    int4* __restrict__ recs = p.recs + pid * p.n_views;
+    uint32_t* __restrict__ mrow = masks + pid * nchunks;
+    uint32_t* __restrict__ H = sp.hdrs + task * (int64_t)sp.cap_stages * 16;
+    const uint32_t rowb16 = (uint32_t)sp.rowb >> 4;
+    int nv = 0, nst = 0;
+    uint32_t m = 0u;
+    int4 rec0 = make_int4(0, 0, 0, 0);
+    for (int v0 = p.v_begin; v0 < p.v_end; v0 += kPsViews) {
+        float zc[kPsViews], d[kPsViews], us[kPsViews], ws[kPsViews];
+        int cand[kPsViews];
+#pragma unroll
+        for (int t = 0; t < kPsViews; ++t) {  // phase 1: project, issue the depth reads (camera loads are uniform)
+            const int v = v0 + t;
+            cand[t] = -1;
+            d[t] = zc[t] = us[t] = ws[t] = 0.f;
+            if (v < p.v_end && has) {
+                const float4 k4 = ldg_f4(p.K4 + 4 * (int64_t)v);
+                const float4 r0 = ldg_f4(p.w2c + 12 * (int64_t)v);
+                const float4 r1 = ldg_f4(p.w2c + 12 * (int64_t)v + 4);
+                const float4 r2 = ldg_f4(p.w2c + 12 * (int64_t)v + 8);
+                zc[t] = project_point(k4, r0, r1, r2, px, py, pz, p.z_near, us[t], ws[t]);
+                if (zc[t] > p.z_near) {
+                    const float uif = floorf(__fadd_rn(us[t], 0.5f));
+                    const float wif = floorf(__fadd_rn(ws[t], 0.5f));
+                    if (uif >= 0.f && uif < wd_f && wif >= 0.f && wif < hd_f) {
+                        cand[t] = (int)wif * p.Wd + (int)uif;
+                        if (p.depth_u16)
+                            d[t] = __fmul_rn((float)__ldg(reinterpret_cast<const uint16_t*>(p.depth) +
+                                                          (int64_t)v * depth_elems + cand[t]),
+                                             0.001f);
+                        else
+                            d[t] = __ldg(reinterpret_cast<const float*>(p.depth) + (int64_t)v * depth_elems + cand[t]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < kPsViews; ++t) {  // phase 2: depth test, mask bit, stages + sample record
+            const int v = v0 + t;
+            if (v >= p.v_end) break;
+            const bool visible = has && cand[t] >= 0 && d[t] > 0.f && fabsf(__fsub_rn(d[t], zc[t])) <= p.tau;
+            if (has) {
+                if (p.pix_idx) p.pix_idx[(int64_t)v * p.N + pid] = visible ? cand[t] : -1;
+                if (p.vis) p.vis[(int64_t)v * p.N + pid] = visible ? 1 : 0;
+            }
+            const int bit = (v - p.v_begin) & 31;
+            if (visible) m |= 1u << bit;
+            if (__any_sync(kFull, visible)) {
+                TapGeom g;
+                g.x0 = g.y0 = 0;
+                g.ax = g.ay = 0.f;
+                g.flags = 0u;
+                if (visible) g = tap_geometry(us[t], ws[t], p.stride, p.inv_stride, p.Hf, p.Wf);
+                int4 rec = make_int4(0, 0, 0, 0);
+                nst += build_view_stages(visible, g.x0, g.y0, g.flags, __float_as_int(g.ax), __float_as_int(g.ay),
+                                         (v * p.Hf + g.y0) * p.Wf + g.x0, v, H + nst * 16, sp.cap_pix, rowb16, lane, rec);
+                if (visible) {
+                    recs[nv] = rec;
+                    if (nv == 0) rec0 = rec;
+                    ++nv;
+                }
+            }
+            if (has && (bit == 31 || v == p.v_end - 1)) {
+                mrow[(v - p.v_begin) >> 5] = m;
+                m = 0u;
+            }
+        }
+    }
+    if (nst == 0) {  // nothing of this run is visible: one empty stage carries the run through the pipeline
+        if (lane < 16) H[lane] = 0u;
+        nst = 1;
+    }
+    if (has) p.nvis[pid] = nv;
+    int4* __restrict__ rp = sp.runpts + (task * 32 + lane) * 2;
+    rp[0] = make_int4(has ? (int)pid : -1, nv, 0, 0);
+    rp[1] = rec0;
+    if (lane == 0) sp.runinfo[task] = make_int4((int)start, npts, seg, nst);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stand-alone stage planner (used when the projection ran without a plan, e.g. concurrently with the plan kernels):
+// one warp per (run, chunk of 8 views), lane = point of the run; re-reads K1's records
 // ---------------------------------------------------------------------------------------------------
 constexpr int kPlanWarps = 4;
 constexpr int kPlanViews = 8;                       // views per planner warp
@@ -128,90 +350,30 @@ __global__ void __launch_bounds__(kPlanWarps * 32) stage_plan_kernel(const LiftP
         below += __popc(mw & ((1u << (v_lo & 31)) - 1u));
         bits = (mw >> (v_lo & 31)) & ((1u << kPlanViews) - 1u);
     }
-    int4* __restrict__ recs = p.recs + (int64_t)max(pid, 0) * p.n_views + below;
-    int4 recv[kPlanViews];  // the lane's record of chunk view i (if visible): all loads in flight together
-#pragma unroll
-    for (int i = 0; i < kPlanViews; ++i) {
-        recv[i] = make_int4(0, 0, 0, 0);
-        if (bits & (1u << i)) recv[i] = recs[__popc(bits & ((1u << i) - 1u))];
-    }
-    uint32_t* __restrict__ H = sp.hdrs + (task * (int64_t)sp.cap_stages + (int64_t)ck * kPlanSlots) * 16;
+    int4* __restrict__ recs = p.recs + (int64_t)max(pid, 0) * p.n_views;
     int nst = 0;
     const uint32_t any = __reduce_or_sync(kFull, bits);
+    if (any) {
+        int4 recv[kPlanViews];  // the lane's record of chunk view i (if visible): all loads in flight together
+#pragma unroll
+        for (int i = 0; i < kPlanViews; ++i) {
+            recv[i] = make_int4(0, 0, 0, 0);
+            if (bits & (1u << i)) recv[i] = recs[below + __popc(bits & ((1u << i) - 1u))];
+        }
+        uint32_t* __restrict__ H = sp.hdrs + (task * (int64_t)sp.cap_stages + (int64_t)ck * kPlanSlots) * 16;
+        const uint32_t rowb16 = (uint32_t)sp.rowb >> 4;
 #pragma unroll 1
-    for (int i = 0; i < kPlanViews; ++i) {
-        if (!((any >> i) & 1u)) continue;
-        int4 rec = make_int4(0, 0, 0, 0);
+        for (int i = 0; i < kPlanViews; ++i) {
+            if (!((any >> i) & 1u)) continue;
+            int4 rec = make_int4(0, 0, 0, 0);
 #pragma unroll
-        for (int j = 0; j < kPlanViews; ++j)
-            if (j == i) rec = recv[j];
-        const int v = p.v_begin + v_lo + i;
-        const int x0 = rec_x0(rec.y), y0 = rec_y0(rec.y);
-        const uint32_t flags = (uint32_t)rec.y & 15u;
-        bool cand = (bits >> i) & 1u;
-        const int ridx = __popc(bits & ((1u << i) - 1u));
-        for (int sub = 0; sub < kStMaxSub; ++sub) {
-            if (!__any_sync(kFull, cand)) break;
-            uint32_t bm[8];
-            int xmin = 0, ymin = 0, npix = 0;
-            bool sel = false;
-            for (int box = 16; box >= 2; box >>= 1) {
-                xmin = __reduce_min_sync(kFull, cand ? x0 : 0x3fffffff);
-                const bool fitx = cand && (x0 - xmin <= box - 2);
-                ymin = __reduce_min_sync(kFull, fitx ? y0 : 0x3fffffff);
-                sel = fitx && (y0 - ymin <= box - 2);
-                const int cx = x0 - xmin, cy = y0 - ymin;  // 0..14 when sel
-                const uint32_t top = sel ? (flags & 3u) << cx : 0u, bot = sel ? ((flags >> 2) & 3u) << cx : 0u;
-                npix = 0;
-#pragma unroll
-                for (int w = 0; w < 8; ++w) {
-                    uint32_t c = 0u;
-                    if ((cy >> 1) == w) c |= top << ((cy & 1) * 16);
-                    if (((cy + 1) >> 1) == w) c |= bot << (((cy + 1) & 1) * 16);
-                    bm[w] = __reduce_or_sync(kFull, c);
-                    npix += __popc(bm[w]);
-                }
-                if (npix <= sp.cap_pix) break;
-            }
-            // slot rank of a tap = number of bitmap bits below it
-            uint32_t ranks = 0u;
-            if (sel) {
-                const int cx = x0 - xmin, cy = y0 - ymin;
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    uint32_t r = kRankZero;
-                    if (flags & (1u << t)) {
-                        const int b = (cy + (t >> 1)) * 16 + cx + (t & 1);
-                        int rk = 0;
-#pragma unroll
-                        for (int w = 0; w < 8; ++w) {
-                            if (w < (b >> 5)) rk += __popc(bm[w]);
-                            if (w == (b >> 5)) rk += __popc(bm[w] & ((1u << (b & 31)) - 1u));
-                        }
-                        r = (uint32_t)rk;
-                    }
-                    ranks |= r << (8 * t);
-                }
-            }
-            const bool direct = (sub == kStMaxSub - 1) && cand && !sel;  // the view's leftovers ride on its last stage
-            const bool member = sel || direct;
-            const uint32_t mask = __ballot_sync(kFull, member);
-            if (lane < 16) {
-                uint32_t wv = 0u;
-                if (lane == 0) wv = (uint32_t)v;
-                if (lane == 1) wv = mask;
-                if (lane == 2) wv = ((uint32_t)xmin & 0xffffu) | ((uint32_t)ymin << 16);
-                if (lane == 3) wv = (uint32_t)npix;
-#pragma unroll
-                for (int w = 0; w < 8; ++w)
-                    if (lane == 4 + w) wv = bm[w];
-                H[nst * 16 + lane] = wv;
-            }
-            if (member) {
-                recs[ridx].y = sel ? (int)ranks : (int)(flags | kRecDirect);
-                cand = false;
-            }
-            ++nst;
+            for (int j = 0; j < kPlanViews; ++j)
+                if (j == i) rec = recv[j];
+            const bool cand = (bits >> i) & 1u;
+            int4 out = rec;
+            nst += build_view_stages(cand, rec_x0(rec.y), rec_y0(rec.y), (uint32_t)rec.y & 15u, rec.z, rec.w, rec.x,
+                                     p.v_begin + v_lo + i, H + nst * 16, sp.cap_pix, rowb16, lane, out);
+            if (cand) recs[below + __popc(bits & ((1u << i) - 1u))] = out;
         }
     }
     // the last warp of the run to finish packs the chunks' headers to the front of the run's header array
@@ -238,11 +400,13 @@ __global__ void __launch_bounds__(kPlanWarps * 32) stage_plan_kernel(const LiftP
         }
         const int dst0 = total + incl - cnt;
         total += __shfl_sync(kFull, incl, 31);
-        for (int l = 0; l < 32; ++l) {  // chunk c0 + l: its headers move from slot (c0+l)*kPlanSlots to dst
+        uint32_t todo = __ballot_sync(kFull, cnt > 0 && dst0 != c * kPlanSlots);
+        while (todo) {  // chunk c0 + l: its headers move from slot (c0 + l) * kPlanSlots to dst (dst < src)
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1u;
             const int n_l = __shfl_sync(kFull, cnt, l), d_l = __shfl_sync(kFull, dst0, l);
             const int s_l = (c0 + l) * kPlanSlots;
-            if (n_l == 0 || d_l == s_l) continue;
-            for (int j0 = 0; j0 < n_l; j0 += 8) {  // 8 headers (4 x 16 bytes each) per pass; dst < src: load all, then store
+            for (int j0 = 0; j0 < n_l; j0 += 8) {  // 8 headers (4 x 16 bytes each) per pass: load all, then store
                 const int j = j0 + (lane >> 2);
                 uint4 val = make_uint4(0u, 0u, 0u, 0u);
                 if (j < n_l) val = __ldcg(HV + (int64_t)(s_l + j) * 4 + (lane & 3));
@@ -255,7 +419,12 @@ __global__ void __launch_bounds__(kPlanWarps * 32) stage_plan_kernel(const LiftP
         if (lane < 4) HV[lane] = make_uint4(0u, 0u, 0u, 0u);
         total = 1;
     }
-    sp.runpts[task * 32 + lane] = make_int2(pid, has ? p.nvis[pid] : 0);
+    const int nv = has ? p.nvis[pid] : 0;
+    int4 rec0 = make_int4(0, 0, 0, 0);
+    if (nv > 0) rec0 = __ldcg(recs);  // as rewritten by the planner warp of view chunk 0
+    int4* __restrict__ rp = sp.runpts + (task * 32 + lane) * 2;
+    rp[0] = make_int4(pid, nv, 0, 0);
+    rp[1] = rec0;
     if (lane == 0) sp.runinfo[task] = make_int4((int)start, npts, seg, total);
 }
 
@@ -264,80 +433,68 @@ __global__ void __launch_bounds__(kPlanWarps * 32) stage_plan_kernel(const LiftP
 // ---------------------------------------------------------------------------------------------------
 struct __align__(16) StageSlot {
     uint4 hdr;        // mask, first ring slot, flags, task
-    uint4 run;        // first processing position, points, segment, -
-    uint4 rec[32];    // the lanes' sample records, translated by the producer:
-                      //   staged: x = off00 | off01 << 16, y = off10 | off11 << 16 (tap row offsets in the ring, / 16)
-                      //   direct: x = pixel index of tap (y0, x0), y = tap-valid flags;  z = ax (sign bit = direct), w = ay
+    uint4 run;        // kStFirst only: first processing position, points, segment, -
+    uint4 rec[32];    // kStFirst only: first sample record of every point of the run
     int32_t pid[32];  // kStFirst only
     int32_t cnt[32];  // kStFirst only: visible views of the point in this call
 };
 
-// the rare sample whose taps are not staged: same loads as gather_kernel, kept out of line so that the unrolled
-// consumer loop stays small (instruction cache)
 template <int NV, typename FT>
-__device__ __noinline__ Sample<NV> direct_taps(const FT* __restrict__ fmap, uint32_t pix, uint32_t flags, int C,
-                                               int row_elems, int lane, unsigned cmask) {
-    constexpr int kE = Tap<FT>::kElems, kR = Tap<FT>::kRegs;
-    Sample<NV> s;
-    sample_clear<NV>(s);
-    const FT* __restrict__ p00 = fmap + (int64_t)(int)pix * C + lane * kE;
-    const FT* __restrict__ p10 = p00 + row_elems;
-#pragma unroll
-    for (int l = 0; l < NV / kR; ++l) {
-        if (!((cmask >> l) & 1u)) continue;
-        if (flags & 1u) Tap<FT>::load(&s.t00[l * kR], p00 + l * 32 * kE);
-        if (flags & 2u) Tap<FT>::load(&s.t01[l * kR], p00 + C + l * 32 * kE);
-        if (flags & 4u) Tap<FT>::load(&s.t10[l * kR], p10 + l * 32 * kE);
-        if (flags & 8u) Tap<FT>::load(&s.t11[l * kR], p10 + C + l * 32 * kE);
-    }
-    return s;
-}
-
-template <int NV, typename FT>
-__device__ __forceinline__ void staged_issue(Sample<NV>& s, const uint4 r, const uint8_t* __restrict__ lane_base,
-                                             const FT* __restrict__ fmap, int C, int row_elems, int lane,
-                                             unsigned cmask) {
+__device__ __forceinline__ void staged_issue(Sample<NV>& s, const uint4 r, const uint8_t* __restrict__ stage_ptr,
+                                             const uint8_t* __restrict__ zero_ptr, const FT* __restrict__ fmap, int C,
+                                             int row_elems, int lane, unsigned cmask) {
     constexpr int kR = Tap<FT>::kRegs;
-    const float ax = __uint_as_float(r.z & 0x7fffffffu), ay = __uint_as_float(r.w);  // ax >= 0: its sign bit = direct
+    const float ax = __uint_as_float(r.z & ~kSignBit), ay = __uint_as_float(r.w & ~kSignBit);
     const float omx = __fsub_rn(1.0f, ax), omy = __fsub_rn(1.0f, ay);
     s.w00 = __fmul_rn(omx, omy);
     s.w01 = __fmul_rn(ax, omy);
     s.w10 = __fmul_rn(omx, ay);
     s.w11 = __fmul_rn(ax, ay);
-    if (r.z & kRecDirect) {  // warp-uniform, rare
-        const Sample<NV> d = direct_taps<NV, FT>(fmap, r.x, r.y & 0xFu, C, row_elems, lane, cmask);
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            s.t00[k] = d.t00[k];
-            s.t01[k] = d.t01[k];
-            s.t10[k] = d.t10[k];
-            s.t11[k] = d.t11[k];
-        }
-    } else {
-        const uint8_t* __restrict__ p00 = lane_base + ((r.x & 0xffffu) << 4);
-        const uint8_t* __restrict__ p01 = lane_base + ((r.x >> 16) << 4);
-        const uint8_t* __restrict__ p10 = lane_base + ((r.y & 0xffffu) << 4);
-        const uint8_t* __restrict__ p11 = lane_base + ((r.y >> 16) << 4);
+    if (r.z & kSignBit) {  // warp-uniform, rare: taps from global memory (predicated loads, zero outside the map)
+        constexpr int kE = Tap<FT>::kElems;
+        const FT* __restrict__ g00 = fmap + (int64_t)(int)r.x * C + lane * kE;
+        const FT* __restrict__ g10 = g00 + row_elems;
 #pragma unroll
         for (int l = 0; l < NV / kR; ++l) {
-            if (cmask & (1u << l)) {
-                if constexpr (kR == 1) {
-                    s.t00[l] = *reinterpret_cast<const float4*>(p00 + l * 512);
-                    s.t01[l] = *reinterpret_cast<const float4*>(p01 + l * 512);
-                    s.t10[l] = *reinterpret_cast<const float4*>(p10 + l * 512);
-                    s.t11[l] = *reinterpret_cast<const float4*>(p11 + l * 512);
-                } else {
-                    Tap<FT>::decode(&s.t00[l * kR], *reinterpret_cast<const uint4*>(p00 + l * 512));
-                    Tap<FT>::decode(&s.t01[l * kR], *reinterpret_cast<const uint4*>(p01 + l * 512));
-                    Tap<FT>::decode(&s.t10[l * kR], *reinterpret_cast<const uint4*>(p10 + l * 512));
-                    Tap<FT>::decode(&s.t11[l * kR], *reinterpret_cast<const uint4*>(p11 + l * 512));
-                }
+#pragma unroll
+            for (int j = 0; j < kR; ++j) s.t00[l * kR + j] = s.t01[l * kR + j] = s.t10[l * kR + j] = s.t11[l * kR + j] = f4_zero();
+            const bool cok = (cmask >> l) & 1u;
+            if (cok && (r.y & 1u)) Tap<FT>::load(&s.t00[l * kR], g00 + l * 32 * kE);
+            if (cok && (r.y & 2u)) Tap<FT>::load(&s.t01[l * kR], g00 + C + l * 32 * kE);
+            if (cok && (r.y & 4u)) Tap<FT>::load(&s.t10[l * kR], g10 + l * 32 * kE);
+            if (cok && (r.y & 8u)) Tap<FT>::load(&s.t11[l * kR], g10 + C + l * 32 * kE);
+        }
+        return;
+    }
+    const uint8_t* __restrict__ p00 = stage_ptr + ((r.x & 0xffffu) << 4);
+    const uint8_t* __restrict__ p01 = stage_ptr + ((r.x >> 16) << 4);
+    const uint8_t* __restrict__ p10 = stage_ptr + ((r.y & 0xffffu) << 4);
+    const uint8_t* __restrict__ p11 = stage_ptr + ((r.y >> 16) << 4);
+    if (r.w & kSignBit) {  // warp-uniform, map border only: taps outside the map read the zero row
+        if ((r.x & 0xffffu) == kOffZero) p00 = zero_ptr;
+        if ((r.x >> 16) == kOffZero) p01 = zero_ptr;
+        if ((r.y & 0xffffu) == kOffZero) p10 = zero_ptr;
+        if ((r.y >> 16) == kOffZero) p11 = zero_ptr;
+    }
+#pragma unroll
+    for (int l = 0; l < NV / kR; ++l) {
+        if (cmask & (1u << l)) {
+            if constexpr (kR == 1) {
+                s.t00[l] = *reinterpret_cast<const float4*>(p00 + l * 512);
+                s.t01[l] = *reinterpret_cast<const float4*>(p01 + l * 512);
+                s.t10[l] = *reinterpret_cast<const float4*>(p10 + l * 512);
+                s.t11[l] = *reinterpret_cast<const float4*>(p11 + l * 512);
+            } else {
+                Tap<FT>::decode(&s.t00[l * kR], *reinterpret_cast<const uint4*>(p00 + l * 512));
+                Tap<FT>::decode(&s.t01[l * kR], *reinterpret_cast<const uint4*>(p01 + l * 512));
+                Tap<FT>::decode(&s.t10[l * kR], *reinterpret_cast<const uint4*>(p10 + l * 512));
+                Tap<FT>::decode(&s.t11[l * kR], *reinterpret_cast<const uint4*>(p11 + l * 512));
             }
         }
     }
 }
 
-// FULL: C fills all NV register vectors of every lane (C = 128 * NV fp32 / 256 * NV / 2 16-bit): no channel predicates
+// FULL: C fills all NV register vectors of every lane (C = 128 * NV): no channel predicates
 template <int NV, typename FT, bool FAST, int PTS, bool DB, bool FULL>
 __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
     gather_staged_kernel(const __grid_constant__ LiftParams p, const __grid_constant__ StagedParams sp) {
@@ -346,14 +503,15 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     const int rowb = p.C * (int)sizeof(FT);
     const int ring = sp.ring_slots;
-    // shared memory: ring rows | zero row | stage slots | barriers | producer scratch | reduce scratch
+    // shared memory: ring rows | zero row | stage slots | barriers | producer scratch | record scratch | reduce scratch
     uint8_t* const ring_ptr = smem;
     StageSlot* const slots = reinterpret_cast<StageSlot*>(smem + (size_t)(ring + 1) * rowb);
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(slots + kStQ);  // full[kStQ], empty[kStQ]
-    uint32_t* const hch = reinterpret_cast<uint32_t*>(bars + 2 * kStQ);  // 8 headers x 16 words
-    int32_t* const ext = reinterpret_cast<int32_t*>(hch + 128);          // ring slots held by stage entry q
-    float4* const sred = reinterpret_cast<float4*>(ext + 16);            // [2][WARPS][NV*32]
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(slots + kStQ);        // full[kStQ], empty[kStQ], red_full, red_empty
+    uint32_t* const hch = reinterpret_cast<uint32_t*>(bars + 2 * kStQ + 2);  // 8 headers x 16 words
+    int32_t* const ext = reinterpret_cast<int32_t*>(hch + 128);              // ring slots held by stage entry q
+    float4* const sred = reinterpret_cast<float4*>(ext + 16);                // [WARPS][NV*32]
     const uint32_t full0 = smem_addr(bars), empty0 = smem_addr(bars + kStQ);
+    const uint32_t red_full = smem_addr(bars + 2 * kStQ), red_empty = red_full + 8;
 
     for (int i = threadIdx.x; i < rowb / 16; i += blockDim.x)
         reinterpret_cast<uint4*>(ring_ptr + (size_t)ring * rowb)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -362,6 +520,8 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
             mbar_init(full0 + 8 * q, 1);
             mbar_init(empty0 + 8 * q, WARPS);
         }
+        mbar_init(red_full, WARPS - 1);
+        mbar_init(red_empty, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -372,7 +532,6 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
     if (warp == WARPS) {
         // ------------------------------------------------ producer ------------------------------------------------
         const uint32_t ring_s = smem_addr(ring_ptr);
-        const uint32_t zero_off = (uint32_t)(ring * rowb) >> 4;
         int n = 0, tail_n = 0, head = 0, free_slots = ring;
         // entry / ring allocation: FIFO over the consumers' `empty` barriers (warp-uniform)
         auto acquire = [&](int npix) -> int {
@@ -392,7 +551,7 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
             __syncwarp();
             return base;
         };
-        // run pipeline: c_next = ticket of the run after the current one, its descriptors are loaded one run ahead
+        // run pipeline: c_next = ticket of the run after the current one; its descriptors are loaded one run ahead
         int c_cur = 0, c_next = 0;
         if (lane == 0) {
             c_cur = atomicAdd(sp.counter, 1);
@@ -402,32 +561,32 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
         c_next = __shfl_sync(kFull, c_next, 0);
         auto task_of = [&](int c) -> int64_t { return ((int64_t)c + sp.task_rot) % n_tasks; };
         const int hlanes = min(8, sp.cap_stages) * 4;
-        int4 ri = make_int4(0, 0, 0, 0);
-        int2 rp = make_int2(-1, 0);
+        int4 ri = make_int4(0, 0, 0, 0), rpa = make_int4(-1, 0, 0, 0), rec0 = make_int4(0, 0, 0, 0);
         uint4 hc = make_uint4(0u, 0u, 0u, 0u);
         if (c_cur < n_tasks) {
             const int64_t t = task_of(c_cur);
             ri = sp.runinfo[t];
-            rp = sp.runpts[t * 32 + lane];
+            rpa = sp.runpts[(t * 32 + lane) * 2];
+            rec0 = sp.runpts[(t * 32 + lane) * 2 + 1];
             if (lane < hlanes) hc = reinterpret_cast<const uint4*>(sp.hdrs + t * (int64_t)sp.cap_stages * 16)[lane];
         }
         while (c_cur < n_tasks) {
             const int64_t task = task_of(c_cur);
-            const int nst = ri.w, pid = rp.x, nv = rp.y;
-            const int4* __restrict__ recs = p.recs + (int64_t)max(pid, 0) * p.n_views;
+            const int nst = ri.w, nv = rpa.y;
             const uint4* __restrict__ hsrc = reinterpret_cast<const uint4*>(sp.hdrs + task * (int64_t)sp.cap_stages * 16);
+            // lane = point of the run: its next sample record (the first one came with the run descriptor)
+            const int4* __restrict__ recs = p.recs + (int64_t)max(rpa.x, 0) * p.n_views;
+            int4 rec = rec0;
             int k = 0;
-            int4 rec = make_int4(0, 0, 0, 0);
-            if (k < nv) rec = recs[0];
             // prefetch the next run's descriptors and the ticket after it
             const int c_after_l = (lane == 0) ? atomicAdd(sp.counter, 1) : 0;
-            int4 ri_n = make_int4(0, 0, 0, 0);
-            int2 rp_n = make_int2(-1, 0);
+            int4 ri_n = make_int4(0, 0, 0, 0), rpa_n = make_int4(-1, 0, 0, 0), rec0_n = make_int4(0, 0, 0, 0);
             uint4 hc_n = make_uint4(0u, 0u, 0u, 0u);
             if (c_next < n_tasks) {
                 const int64_t t = task_of(c_next);
                 ri_n = sp.runinfo[t];
-                rp_n = sp.runpts[t * 32 + lane];
+                rpa_n = sp.runpts[(t * 32 + lane) * 2];
+                rec0_n = sp.runpts[(t * 32 + lane) * 2 + 1];
                 if (lane < hlanes) hc_n = reinterpret_cast<const uint4*>(sp.hdrs + t * (int64_t)sp.cap_stages * 16)[lane];
             }
             for (int s0 = 0; s0 < nst; s0 += 8) {
@@ -439,64 +598,44 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
                     hc = (lane < min(8, nst - s0 - 8) * 4) ? hsrc[(s0 + 8) * 4 + lane] : make_uint4(0u, 0u, 0u, 0u);
                 for (int s = 0; s < cnt8; ++s) {
                     const uint32_t* Hd = hch + s * 16;
-                    const uint32_t view = Hd[0], mask = Hd[1], xy = Hd[2];
-                    const int npix = (int)Hd[3];
-                    const int xmin = (int)(int16_t)(xy & 0xffffu), ymin = (int)(int16_t)(xy >> 16);
+                    const uint4 h0 = *reinterpret_cast<const uint4*>(Hd);  // view, mask, box origin, pixels
+                    const int npix = (int)h0.w;
+                    const int xmin = (int)(int16_t)(h0.z & 0xffffu), ymin = (int)(int16_t)(h0.z >> 16);
                     const int q = n % kStQ;
                     const int base = acquire(npix);
                     StageSlot& S = slots[q];
                     const uint32_t flags = ((s0 + s == 0) ? kStFirst : 0u) | ((s0 + s == nst - 1) ? kStLast : 0u);
                     if (flags & kStFirst) {
-                        S.pid[lane] = pid;
+                        S.pid[lane] = rpa.x;
                         S.cnt[lane] = nv;
                         if (lane == 0) S.run = make_uint4((uint32_t)ri.x, (uint32_t)ri.y, (uint32_t)ri.z, 0u);
                     }
-                    if ((mask >> lane) & 1u) {
-                        uint4 r = make_uint4((uint32_t)rec.x, (uint32_t)rec.y, (uint32_t)rec.z, (uint32_t)rec.w);
-                        if (r.y & kRecDirect) {
-                            r.z |= kRecDirect;
-                        } else {  // slot ranks -> byte offsets / 16 inside the ring (the zero row sits behind it)
-                            const uint32_t rk = r.y;
-                            uint32_t o[4];
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                const uint32_t b = (rk >> (8 * t)) & 0xffu;
-                                o[t] = b == kRankZero ? zero_off : ((uint32_t)(base + (int)b) * (uint32_t)rowb) >> 4;
-                            }
-                            r.x = o[0] | (o[1] << 16);
-                            r.y = o[2] | (o[3] << 16);
-                        }
-                        S.rec[lane] = r;
-                        ++k;
-                        if (k < nv) rec = recs[k];
+                    if ((h0.y >> lane) & 1u) {
+                        S.rec[lane] = make_uint4((uint32_t)rec.x, (uint32_t)rec.y, (uint32_t)rec.z, (uint32_t)rec.w);
+                        if (++k < nv) rec = recs[k];
                     }
                     __syncwarp();
                     const uint32_t fullb = full0 + 8 * q;
                     if (lane == 0) {
-                        S.hdr = make_uint4(mask, (uint32_t)base, flags, (uint32_t)task);
+                        S.hdr = make_uint4(h0.y, (uint32_t)base, flags, (uint32_t)task);
                         mbar_arrive_expect_tx(fullb, (uint32_t)npix * (uint32_t)rowb);
                     }
                     __syncwarp();
-                    if (npix > 0) {  // bitmap rows -> runs of consecutive pixels -> one bulk copy each
-                        const int r = lane & 15;
-                        uint32_t bits = lane < 16 ? (Hd[4 + (r >> 1)] >> ((r & 1) * 16)) & 0xffffu : 0u;
-                        int rowbase = __popc(bits);
-#pragma unroll
-                        for (int o = 1; o < 16; o <<= 1) {
-                            const int up = __shfl_up_sync(kFull, rowbase, o);
-                            if (lane >= o) rowbase += up;
-                        }
-                        rowbase -= __popc(bits);  // exclusive
-                        const uint8_t* src_row = reinterpret_cast<const uint8_t*>(fmap) +
-                                                 (((int64_t)view * p.Hf + (ymin + r)) * p.Wf + xmin) * (int64_t)rowb;
-                        const uint32_t dst_row = ring_s + (uint32_t)(base + rowbase) * (uint32_t)rowb;
-                        const uint32_t orig = bits;
-                        while (bits) {
-                            const int st = __ffs(bits) - 1;
-                            const int len = __ffs(~(bits >> st)) - 1;
-                            bulk_copy_g2s(dst_row + (uint32_t)__popc(orig & ((1u << st) - 1u)) * (uint32_t)rowb,
-                                          src_row + (int64_t)st * rowb, (uint32_t)len * (uint32_t)rowb, fullb);
-                            bits &= ~(((1u << len) - 1u) << st);
+                    if (npix > 0 && lane < 16) {  // bitmap rows -> runs of consecutive pixels -> one bulk copy each
+                        const int r = lane;
+                        uint32_t bits = (Hd[4 + (r >> 1)] >> ((r & 1) * 16)) & 0xffffu;
+                        if (bits) {
+                            const uint32_t rowbase = (Hd[12 + (r >> 2)] >> (8 * (r & 3))) & 0xffu;
+                            const uint8_t* src_row = reinterpret_cast<const uint8_t*>(fmap) +
+                                                     (((int64_t)h0.x * p.Hf + (ymin + r)) * p.Wf + xmin) * (int64_t)rowb;
+                            uint32_t dst = ring_s + ((uint32_t)base + rowbase) * (uint32_t)rowb;
+                            while (bits) {
+                                const int st = __ffs(bits) - 1;
+                                const int len = __ffs(~(bits >> st)) - 1;
+                                bulk_copy_g2s(dst, src_row + (int64_t)st * rowb, (uint32_t)len * (uint32_t)rowb, fullb);
+                                dst += (uint32_t)len * (uint32_t)rowb;
+                                bits &= ~(((1u << len) - 1u) << st);
+                            }
                         }
                     }
                     ++n;
@@ -505,7 +644,8 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
             c_cur = c_next;
             c_next = __shfl_sync(kFull, c_after_l, 0);
             ri = ri_n;
-            rp = rp_n;
+            rpa = rpa_n;
+            rec0 = rec0_n;
             hc = hc_n;
         }
         // exit marker
@@ -522,14 +662,13 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
     const int row_elems = p.Wf * p.C;
     const unsigned cmask = FULL ? 0xffffffffu : channel_mask<FT, NV>(p.C, lane);
     const uint8_t* const lane_base = ring_ptr + lane * 16;
+    const uint8_t* const zero_ptr = lane_base + (size_t)ring * rowb;
     float4 acc[PTS][NV];
     Sample<NV> sa, sb;
     sample_clear<NV>(sa);
     if (DB) sample_clear<NV>(sb);
     int my_pid = -1, my_cnt = 0;  // lane t < PTS: the t-th point of this warp = point warp + WARPS * t of the run
-    int64_t run_start = 0;
-    int run_seg = -1, run_parity = 0;
-    int64_t run_task = 0;
+    int run_start = 0, run_seg = -1, run_task = 0, red_n = 0;
     for (int n = 0;; ++n) {
         const int q = n % kStQ;
         mbar_wait(full0 + 8 * q, (uint32_t)((n / kStQ) & 1));
@@ -538,12 +677,13 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
         if (h.z & kStExit) break;
         if (h.z & kStFirst) {
             const uint4 hr = S.run;
-            run_start = (int64_t)(int)hr.x;
+            run_start = (int)hr.x;
             run_seg = (int)hr.z;
-            run_task = (int64_t)h.w;
+            run_task = (int)h.w;
             const int j = warp + WARPS * lane;
-            my_pid = (lane < PTS && j < (int)hr.y) ? S.pid[j] : -1;
-            my_cnt = (lane < PTS && j < (int)hr.y) ? S.cnt[j] : 0;
+            const bool mine = lane < PTS && j < (int)hr.y;
+            my_pid = mine ? S.pid[j] : -1;
+            my_cnt = mine ? S.cnt[j] : 0;
 #pragma unroll
             for (int t = 0; t < PTS; ++t) {
 #pragma unroll
@@ -551,14 +691,14 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
             }
             if (p.accumulate) {
                 if (my_pid >= 0) {
-                    const int64_t orow = p.by_pos ? run_start + warp + WARPS * lane : (int64_t)my_pid;
+                    const int64_t orow = p.by_pos ? (int64_t)run_start + warp + WARPS * lane : (int64_t)my_pid;
                     my_cnt += p.count[orow];
                 }
 #pragma unroll
                 for (int t = 0; t < PTS; ++t) {
                     const int pt = __shfl_sync(kFull, my_pid, t);
                     if (pt >= 0) {
-                        const int64_t orow = p.by_pos ? run_start + warp + WARPS * t : (int64_t)pt;
+                        const int64_t orow = p.by_pos ? (int64_t)run_start + warp + WARPS * t : (int64_t)pt;
 #pragma unroll
                         for (int k = 0; k < NV; ++k) {
                             const int c = chan_of<FT>(k, lane);
@@ -569,21 +709,22 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
             }
         }
         const uint32_t wbits = h.x >> warp;  // bit WARPS * t = this warp's t-th point is in the stage
+        const uint8_t* const stage_ptr = lane_base + h.y * (uint32_t)rowb;
         if (DB) {
             // two samples in flight: the taps of the next owned point are requested before the current one is blended
-            if (wbits & 1u) staged_issue<NV, FT>(sa, S.rec[warp], lane_base, fmap, p.C, row_elems, lane, cmask);
+            if (wbits & 1u) staged_issue<NV, FT>(sa, S.rec[warp], stage_ptr, zero_ptr, fmap, p.C, row_elems, lane, cmask);
 #pragma unroll
             for (int t = 0; t < PTS; ++t) {
                 if (t + 1 < PTS && ((wbits >> (WARPS * (t + 1))) & 1u))
-                    staged_issue<NV, FT>((t & 1) ? sa : sb, S.rec[warp + WARPS * (t + 1)], lane_base, fmap, p.C, row_elems,
-                                         lane, cmask);
+                    staged_issue<NV, FT>((t & 1) ? sa : sb, S.rec[warp + WARPS * (t + 1)], stage_ptr, zero_ptr, fmap, p.C,
+                                         row_elems, lane, cmask);
                 if ((wbits >> (WARPS * t)) & 1u) sample_accum<NV, FAST>(acc[t], (t & 1) ? sb : sa);
             }
         } else {
 #pragma unroll
             for (int t = 0; t < PTS; ++t) {
                 if ((wbits >> (WARPS * t)) & 1u) {
-                    staged_issue<NV, FT>(sa, S.rec[warp + WARPS * t], lane_base, fmap, p.C, row_elems, lane, cmask);
+                    staged_issue<NV, FT>(sa, S.rec[warp + WARPS * t], stage_ptr, zero_ptr, fmap, p.C, row_elems, lane, cmask);
                     sample_accum<NV, FAST>(acc[t], sa);
                 }
             }
@@ -600,7 +741,7 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
                 const int pt = __shfl_sync(kFull, my_pid, t);
                 const int cnt = __shfl_sync(kFull, my_cnt, t);
                 if (pt < 0) continue;
-                const int64_t i = run_start + warp + WARPS * t;
+                const int64_t i = (int64_t)run_start + warp + WARPS * t;
                 const int64_t orow = p.by_pos ? i : (int64_t)pt;
                 float* out_row = p.out + orow * p.C;
                 int32_t* cnt_dst = p.count + orow;
@@ -625,34 +766,42 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
                 if (lane == 0) *cnt_dst = cnt;
             }
             if (p.pool && run_seg < p.S) {  // uniform over the consumer warps
-                float4* red = sred + (size_t)run_parity * WARPS * NV * 32;
+                // warp 0 adds the warps' rows in warp order. Hand-off through two mbarriers, so that a warp only ever
+                // waits for what it really depends on: warp 0 for the seven rows, the others for warp 0 having read
+                // their previous row before they overwrite it.
+                if (warp != 0 && red_n > 0) mbar_wait(red_empty, (uint32_t)((red_n - 1) & 1));
 #pragma unroll
-                for (int k = 0; k < NV; ++k) red[(warp * NV + k) * 32 + lane] = sp_acc[k];
-                asm volatile("bar.sync 1, %0;" ::"r"(WARPS * 32) : "memory");
-                if (warp == 0) {
+                for (int k = 0; k < NV; ++k) sred[(warp * NV + k) * 32 + lane] = sp_acc[k];
+                __syncwarp();
+                if (warp != 0) {
+                    if (lane == 0) mbar_arrive(red_full);
+                } else {
+                    mbar_wait(red_full, (uint32_t)(red_n & 1));
 #pragma unroll
                     for (int k = 0; k < NV; ++k) {
-                        float4 tsum = red[k * 32 + lane];
+                        float4 tsum = sred[k * 32 + lane];
 #pragma unroll
-                        for (int w = 1; w < WARPS; ++w) tsum = f4_add(tsum, red[(w * NV + k) * 32 + lane]);
+                        for (int w = 1; w < WARPS; ++w) tsum = f4_add(tsum, sred[(w * NV + k) * 32 + lane]);
                         const int c = chan_of<FT>(k, lane);
                         if (FULL || c < p.C) *reinterpret_cast<float4*>(p.partials + run_task * (int64_t)p.C + c) = tsum;
                     }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(red_empty);
                 }
-                run_parity ^= 1;
+                ++red_n;
             }
         }
     }
 }
 
 size_t staged_smem_bytes(int ring_slots, int rowb, int warps, int nv) {
-    return (size_t)(ring_slots + 1) * rowb + sizeof(StageSlot) * kStQ + 2 * kStQ * 8 + 128 * 4 + 16 * 4 +
-           (size_t)2 * warps * nv * 32 * 16;
+    return (size_t)(ring_slots + 1) * rowb + sizeof(StageSlot) * kStQ + (2 * kStQ + 2) * 8 + 128 * 4 + 16 * 4 +
+           (size_t)warps * nv * 32 * 16;
 }
 
 template <int NV, typename FT, int PTS>
-static int launch_staged(const LiftParams& p, StagedParams sp, int variant, bool do_plan, bool do_gather,
-                         cudaStream_t stream) {
+static int launch_staged(const LiftParams& p, StagedParams sp, int variant, int plan_mode, uint32_t* masks,
+                         bool do_gather, cudaStream_t stream) {
     constexpr int WARPS = 32 / PTS;
     const int rowb = p.C * (int)sizeof(FT);
     // two CTAs per SM share 228 KB (1 KB of each is reserved by the system)
@@ -661,13 +810,16 @@ static int launch_staged(const LiftParams& p, StagedParams sp, int variant, bool
     const int ring = (int)((budget - fixed) / rowb);
     if (ring < 8) return SD3D_ERR_UNSUPPORTED;
     sp.ring_slots = ring;
-    sp.cap_pix = min(ring / 2, 126);  // slot ranks travel as bytes inside the records (0x7F = outside the map)
+    sp.cap_pix = min(ring / 2, 255);  // the header's row-prefix counts are bytes
+    sp.rowb = rowb;
     const size_t smem = staged_smem_bytes(ring, rowb, WARPS, NV);
     const bool fast = (variant & 1) != 0, db = (variant & 4) != 0;
     const bool full = p.C == 128 * NV;  // every lane's NV register vectors hold channels (fp32: 4 each, 16-bit: 8 per 2)
     const int64_t plan_tasks = p.pool ? sp.max_tasks : sp.n_tasks;
     const int nck = (p.n_views + kPlanViews - 1) / kPlanViews;
-    if (do_plan)
+    if (plan_mode == 2)  // projection + stage planning in one pass over the runs
+        project_stage_kernel<<<(unsigned)ceil_div64(plan_tasks, kPsWarps), kPsWarps * 32, 0, stream>>>(p, masks, sp.nchunks, sp);
+    else if (plan_mode == 1)  // records of an earlier projection-only call
         stage_plan_kernel<<<(unsigned)ceil_div64(plan_tasks * nck, kPlanWarps), kPlanWarps * 32, 0, stream>>>(p, sp);
     if (!do_gather) return SD3D_OK;
     const unsigned grid = (unsigned)imin64(plan_tasks, (int64_t)2 * num_sms());
@@ -693,21 +845,21 @@ static int launch_staged(const LiftParams& p, StagedParams sp, int variant, bool
 }
 
 template <typename FT>
-static int dispatch_staged_t(const LiftParams& p, const StagedParams& sp, int variant, bool do_plan, bool do_gather,
-                             cudaStream_t stream) {
+static int dispatch_staged_t(const LiftParams& p, const StagedParams& sp, int variant, int plan_mode, uint32_t* masks,
+                             bool do_gather, cudaStream_t stream) {
     constexpr int kR = Tap<FT>::kRegs;
     const int nv = kR == 1 ? (p.C + 127) / 128 : 2 * ((p.C + 255) / 256);
     const bool narrow = (variant & 8) != 0;  // 4 consumer warps x 8 points instead of 8 x 4
     if (nv == 1) {
         if constexpr (kR == 1)
-            return narrow ? launch_staged<1, FT, 8>(p, sp, variant, do_plan, do_gather, stream)
-                          : launch_staged<1, FT, 4>(p, sp, variant, do_plan, do_gather, stream);
+            return narrow ? launch_staged<1, FT, 8>(p, sp, variant, plan_mode, masks, do_gather, stream)
+                          : launch_staged<1, FT, 4>(p, sp, variant, plan_mode, masks, do_gather, stream);
         return SD3D_ERR_UNSUPPORTED;
     }
     if (nv == 2)
-        return narrow ? launch_staged<2, FT, 8>(p, sp, variant, do_plan, do_gather, stream)
-                      : launch_staged<2, FT, 4>(p, sp, variant, do_plan, do_gather, stream);
-    if (nv <= 4) return launch_staged<4, FT, 4>(p, sp, variant, do_plan, do_gather, stream);
+        return narrow ? launch_staged<2, FT, 8>(p, sp, variant, plan_mode, masks, do_gather, stream)
+                      : launch_staged<2, FT, 4>(p, sp, variant, plan_mode, masks, do_gather, stream);
+    if (nv <= 4) return launch_staged<4, FT, 4>(p, sp, variant, plan_mode, masks, do_gather, stream);
     return SD3D_ERR_UNSUPPORTED;
 }
 
@@ -722,7 +874,7 @@ static size_t staged_cap_stages(int n_views) { return (size_t)((n_views + kPlanV
 
 size_t staged_workspace_bytes(int64_t tasks, int n_views) {
     const size_t nck = (size_t)(n_views + kPlanViews - 1) / kPlanViews;
-    return (size_t)tasks * staged_cap_stages(n_views) * 64 + (size_t)tasks * 16 + (size_t)tasks * 32 * 8 +
+    return (size_t)tasks * staged_cap_stages(n_views) * 64 + (size_t)tasks * 16 + (size_t)tasks * 32 * 32 +
            (size_t)tasks * nck * 4 + (size_t)tasks * 4 + 256;
 }
 
@@ -734,8 +886,8 @@ void staged_carve(void* base, int64_t tasks, int n_views, StagedParams& sp) {
     b += (size_t)tasks * sp.cap_stages * 64;
     sp.runinfo = reinterpret_cast<int4*>(b);
     b += (size_t)tasks * 16;
-    sp.runpts = reinterpret_cast<int2*>(b);
-    b += (size_t)tasks * 32 * 8;
+    sp.runpts = reinterpret_cast<int4*>(b);
+    b += (size_t)tasks * 32 * 32;
     sp.chunk_cnt = reinterpret_cast<int32_t*>(b);
     b += (size_t)tasks * nck * 4;
     sp.done = reinterpret_cast<int32_t*>(b);
@@ -744,12 +896,12 @@ void staged_carve(void* base, int64_t tasks, int n_views, StagedParams& sp) {
     sp.n_done = tasks;
 }
 
-int dispatch_staged(const LiftParams& p, const StagedParams& sp, int fmap_dtype, int variant, bool do_plan,
-                    bool do_gather, cudaStream_t stream) {
+int dispatch_staged(const LiftParams& p, const StagedParams& sp, int fmap_dtype, int variant, int plan_mode,
+                    uint32_t* masks, bool do_gather, cudaStream_t stream) {
     switch (fmap_dtype) {
-        case SD3D_F32: return dispatch_staged_t<float>(p, sp, variant, do_plan, do_gather, stream);
-        case SD3D_F16: return dispatch_staged_t<__half>(p, sp, variant, do_plan, do_gather, stream);
-        case SD3D_BF16: return dispatch_staged_t<__nv_bfloat16>(p, sp, variant, do_plan, do_gather, stream);
+        case SD3D_F32: return dispatch_staged_t<float>(p, sp, variant, plan_mode, masks, do_gather, stream);
+        case SD3D_F16: return dispatch_staged_t<__half>(p, sp, variant, plan_mode, masks, do_gather, stream);
+        case SD3D_BF16: return dispatch_staged_t<__nv_bfloat16>(p, sp, variant, plan_mode, masks, do_gather, stream);
     }
     return SD3D_ERR_UNSUPPORTED;
 }

@@ -26,6 +26,7 @@ from . import _lib
 from ._lib import Sd3dError, check
 
 DEFAULT_RUN = 32
+STAGED = 32768  # sd3d_lift variant bit 15: shared-memory staged gather (include/sd3d.h)
 TAU_DEFAULT = 0.05
 Z_NEAR_DEFAULT = 0.1
 
@@ -326,7 +327,11 @@ class _LiftLaunch:
             self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev)
 
     def call(self, stage_bits: int, plan: Optional[SuperpointPlan]) -> None:
-        """stage_bits: 0 = projection + gather, 256 = projection only, 512 = gather only."""
+        """stage_bits: 0 = projection + gather, 256 = projection only (with a plan it also cuts the stages of the
+        shared-memory gather), 512 = gather only after a projection WITHOUT plan (stage planner + gather),
+        4096 = stage planner only, 8192 = gather only (stages are planned)."""
+        if stage_bits == 256:
+            self.projected_with_plan = plan is not None
         with torch.cuda.device(self.dev):
             check(self.lib.sd3d_lift(
                 _ptr(self.xyz), self.n, _ptr(self.K), _ptr(self.w2c), self.v, self.vb, self.ve, _ptr(self.depth),
@@ -351,11 +356,13 @@ class _LiftLaunch:
 def _timed_gather(L: "_LiftLaunch", plan, events) -> None:
     """bench only. Two events bracket everything after the projection (stage planner + gather); three events
     split it: events[0] | stage planner | events[1] | gather | events[2]."""
+    planned = getattr(L, "projected_with_plan", False)
     events[0].record()
     if len(events) == 2:
-        L.call(512, plan)
+        L.call(8192 if planned else 512, plan)
     else:
-        L.call(4096, plan)
+        if not planned:
+            L.call(4096, plan)
         events[1].record()
         L.call(8192, plan)
     events[-1].record()
@@ -504,7 +511,9 @@ def lift_and_pool(xyz, K, pose_w2c, depth, fmap, sp_ids: torch.Tensor, n_superpo
     max_tasks = int(_lib.load().sd3d_sp_max_tasks(n, int(n_superpoints), run))
     L = _LiftLaunch(xyz, K, pose_w2c, depth, fmap, stride, tau, z_near, None, True, True, False, None, variant,
                     n_superpoints, max_tasks, run)
-    if overlap and n > 0:
+    # For the shared-memory staged gather (variant bit 15) the projection kernel also cuts the stages, which needs the
+    # plan first; the direct gather keeps the order-less projection overlapped with the plan kernels.
+    if overlap and n > 0 and not (variant & STAGED):
         cur = torch.cuda.current_stream(L.dev)
         side = _side_stream(L.dev)
         fork, join = torch.cuda.Event(), torch.cuda.Event()
@@ -521,7 +530,7 @@ def lift_and_pool(xyz, K, pose_w2c, depth, fmap, sp_ids: torch.Tensor, n_superpo
     if events is not None:
         _timed_gather(L, plan, events)
     else:
-        L.call(512, plan)
+        L.call(8192 if L.projected_with_plan else 512, plan)
     L.combine(plan)
     return L.feat, L.count, L.sp_out, plan
 

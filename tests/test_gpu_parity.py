@@ -244,17 +244,17 @@ def test_lift_kernel_variants_bit_exact(variant, run):
     assert rel_row_err(r["sp_feat"], sp_o, floor=0.1) <= 1e-5
 
 
-@pytest.mark.parametrize("variant", [0, 4, 8, 12, 2048])
+@pytest.mark.parametrize("variant", [32768, 32768 + 4, 32768 + 8, 32768 + 12, 0])
 @pytest.mark.parametrize("cfg", [dict(n_points=6000, n_views=40, hd=120, wd=160, stride=8, channels=256, seed=23),
                                  dict(n_points=9000, n_views=13, hd=60, wd=80, stride=4, channels=64, seed=24),
                                  dict(n_points=5000, n_views=5, hd=96, wd=128, stride=2, channels=128, seed=25),
                                  dict(n_points=4000, n_views=3, hd=60, wd=80, stride=4, channels=512, seed=26),
                                  dict(n_points=700, n_views=70, hd=48, wd=64, stride=8, channels=8, seed=27)])
 def test_staged_gather_bit_exact(cfg, variant):
-    """With a plan (run = 32) the gather stages every distinct tap pixel of a (run, view) in shared memory with
-    bulk copies and blends from there (variant 0; bit 2 = two samples in flight, bit 3 = 8 consumer warps x 4
-    points); 2048 forces the direct gather. All of them: integers and fp32 sums bit-identical to the oracle,
-    border taps (small maps: many) read the zero row."""
+    """variant bit 15 (32768): with a plan (run = 32) the gather stages every distinct tap pixel of a (run, view) in
+    shared memory with bulk copies (TMA engine) and blends from there (bit 2 = two samples in flight, bit 3 = 4
+    consumer warps x 8 points instead of 8 x 4); 0 = the direct gather. All of them: integers and fp32 sums
+    bit-identical to the oracle, border taps (small maps: many) read the zero row."""
     sc = make_scene(sp_target=40, **cfg)
     a, c, _, _ = lo.lift_accumulate_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride)
     d = sc.to(DEV)
@@ -275,6 +275,24 @@ def test_staged_gather_bit_exact(cfg, variant):
         assert torch.equal(full["feat"].cpu(), a) and torch.equal(full["count"].cpu(), c)
 
 
+def test_staged_gather_after_orderless_projection():
+    """The projection may run before the plan exists (it is overlapped with the plan kernels): the stand-alone stage
+    planner then re-reads its records (sd3d_lift stage bits 256 -> 512)."""
+    from segdino3d_b200 import ops
+    sc = make_scene(n_points=7000, n_views=21, hd=120, wd=160, stride=8, channels=256, seed=33, sp_target=50)
+    a, c, _, _ = lo.lift_accumulate_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride)
+    d = sc.to(DEV)
+    plan = sd.sp_sort(d.sp_ids, sc.n_superpoints, xyz=d.xyz)
+    L = ops._LiftLaunch(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, ops.TAU_DEFAULT, ops.Z_NEAR_DEFAULT, None, True, True,
+                        False, None, ops.STAGED, plan.n_segments, plan.max_tasks, plan.run)
+    L.call(256, None)
+    L.call(512, plan)
+    L.combine(plan)
+    feat_o = lo.lift_finalize_oracle(a, c)
+    assert torch.equal(L.feat.cpu(), feat_o) and torch.equal(L.count.cpu(), c)
+    assert rel_row_err(L.sp_out, so.scatter_mean_oracle(feat_o, sc.sp_ids, dim=0), floor=0.1) <= 1e-5
+
+
 @pytest.mark.parametrize("fmap_dtype", [torch.float16, torch.bfloat16])
 def test_staged_gather_16bit_maps(fmap_dtype):
     sc = make_scene(n_points=8000, n_views=20, hd=120, wd=160, stride=8, channels=256, seed=31, sp_target=60,
@@ -282,7 +300,7 @@ def test_staged_gather_16bit_maps(fmap_dtype):
     a, c, _, _ = lo.lift_accumulate_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride)
     d = sc.to(DEV)
     plan = sd.sp_sort(d.sp_ids, sc.n_superpoints, xyz=d.xyz)
-    for variant in (0, 4, 8, 2048):
+    for variant in (32768, 32768 + 4, 32768 + 8, 0):
         raw = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan, finalize=False, variant=variant)
         assert torch.equal(raw["count"].cpu(), c) and torch.equal(raw["feat"].cpu(), a), variant
 
