@@ -131,6 +131,23 @@ int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, in
               int64_t S, const int32_t* task_offsets, const int32_t* task_seg, int64_t max_tasks, int run, void* ws,
               size_t ws_bytes, int pool, int variant, void* stream);
 
+/* The whole path of one scene in ONE call: sd3d_sp_plan + sd3d_lift (projection on a library-owned side stream,
+ * concurrent with the plan; fused pooling) + sd3d_sp_combine, all enqueued on `stream` from C++ into caller-owned
+ * buffers. Replaces the per-scene python loop + scatter_mean of SpConvUNet.forward_wrapper
+ * (segdino3d/models/backbone/spconvunet.py:365-395) fed by the lifted features
+ * (segdino3d/datasets/dataset/scannet200.py:219-234). Outputs: out_feat[N,C] = mean over visible views, count[N],
+ * sp_out[S,C] = scatter_mean(out_feat, sp_ids), and the plan (perm / order [N], seg_offsets / task_offsets [S+2],
+ * task_seg [max_tasks = sd3d_sp_max_tasks(N,S,run)]). ws: sd3d_lift_and_pool_workspace_bytes(...) bytes, reusable
+ * across scenes of the same (or smaller) size: the host side of a step is this one call, no allocation.
+ * variant: as sd3d_lift (its stage-selection bits 8..13 are ignored). */
+size_t sd3d_lift_and_pool_workspace_bytes(int64_t N, int64_t S, int n_views, int C, int run);
+int sd3d_lift_and_pool(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, const void* depth,
+                       int depth_dtype, int Hd, int Wd, const void* fmap, int fmap_dtype, int Hf, int Wf, int C,
+                       float stride, float tau, float z_near, const int64_t* sp_ids, int64_t S, int run, float cell,
+                       int32_t* perm, int32_t* order, int32_t* seg_offsets, int32_t* task_offsets, int32_t* task_seg,
+                       int64_t max_tasks, float* out_feat, int32_t* count, float* sp_out, void* ws, size_t ws_bytes,
+                       int variant, void* stream);
+
 /* second half of the fused pooling: sp_out[s,:] = (sum of the run partials of s, in run order) / max(|s|,1) */
 int sd3d_sp_combine(const void* partials, const int32_t* task_offsets, const int32_t* seg_offsets, int64_t S, int C,
                     int run, float* sp_out, void* stream);

@@ -44,6 +44,18 @@ def threads() -> int:
     return int(lib().sd3d_ref_threads())
 
 
+def use_all_host_threads() -> int:
+    """OpenMP team = every CPU this process may run on, whatever OMP_NUM_THREADS says (torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers, which would make the reference arm single-threaded). Returns the team size."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().sd3d_ref_set_threads(ctypes.c_int(max(n, 1)))
+    torch.set_num_threads(max(n, 1))
+    return threads()
+
+
 def lift_ref(xyz, K, w2c, depth, fmap, stride, tau=0.05, z_near=0.1, want_maps=True):
     n, v = xyz.shape[0], K.shape[0]
     hd, wd = depth.shape[1], depth.shape[2]

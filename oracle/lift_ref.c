@@ -64,6 +64,15 @@ int sd3d_ref_threads(void) {
 #endif
 }
 
+/* OpenMP team size of the following calls, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1) */
+void sd3d_ref_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* Appendix A, verbatim loop nest. Outputs: sum[N,C], count[N]; pix_idx[V,N] / vis[V,N] optional (NULL). */
 void sd3d_ref_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, const void* depth,
                    int depth_dtype, int Hd, int Wd, const void* fmap, int fmap_dtype, int Hl, int Wl, int C,

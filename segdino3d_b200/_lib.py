@@ -36,6 +36,15 @@ SYMBOLS = {
                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,                # order out count pix vis
                           c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int,           # seg_off S task_off task_seg max_tasks run
                           c_void_p, c_size_t, c_int, c_int, c_void_p]),                    # ws ws_bytes pool variant stream
+    "sd3d_lift_and_pool_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_int, c_int]),
+    "sd3d_lift_and_pool": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int,             # xyz N K4 w2c V
+                                   c_void_p, c_int, c_int, c_int,                             # depth dtype Hd Wd
+                                   c_void_p, c_int, c_int, c_int, c_int,                      # fmap dtype Hf Wf C
+                                   c_float, c_float, c_float,                                 # stride tau z_near
+                                   c_void_p, c_int64, c_int, c_float,                         # sp_ids S run cell
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,  # perm order seg_off task_off task_seg max_tasks
+                                   c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,          # feat count sp_out ws ws_bytes
+                                   c_int, c_void_p]),                                         # variant stream
     "sd3d_sp_combine": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "sd3d_lift_push": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,   # xyz N K4 w2c V vb ve
                                c_void_p, c_int, c_int, c_int,                                # depth dtype Hd Wd

@@ -15,6 +15,8 @@ void set_error(const char* fmt, ...);
 // returns SD3D_OK or SD3D_ERR_CUDA (recording cudaGetLastError text prefixed by `what`)
 int check_launch(const char* what);
 int num_sms();
+// a library-owned non-blocking side stream of the current device (small pool, round robin; never destroyed); nullptr on error
+cudaStream_t plan_side_stream();
 
 constexpr unsigned kFull = 0xffffffffu;
 

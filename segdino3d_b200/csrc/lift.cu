@@ -642,7 +642,7 @@ static int lift_impl(const float* xyz, int64_t N, const float* K4, const float* 
     const bool do_stage_plan = (variant & (256 | 8192)) == 0;
     if (pool) {
         if (!finalize || S < 0 || max_tasks < sd3d_sp_max_tasks(N, S, run) ||
-            (do_gather && (order == nullptr || seg_offsets == nullptr || task_offsets == nullptr || task_seg == nullptr))) {
+            (do_gather && N > 0 && (order == nullptr || seg_offsets == nullptr || task_offsets == nullptr || task_seg == nullptr))) {
             set_error("sd3d_lift: fused pooling needs finalize=1, order, seg_offsets and the task tables");
             return SD3D_ERR_ARG;
         }

@@ -736,7 +736,7 @@ static int run_tasks(const int32_t* seg_offsets, const int32_t* perm, const floa
 
 // Side streams owned by the library (per device, a few of them so that plans of different caller streams do not
 // serialise behind each other); never destroyed.
-static cudaStream_t plan_side_stream() {
+cudaStream_t plan_side_stream() {
     constexpr int kMaxDev = 64, kPerDev = 4;
     static std::mutex mu;
     static cudaStream_t pool[kMaxDev][kPerDev] = {};

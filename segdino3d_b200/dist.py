@@ -77,14 +77,15 @@ def cuda_ops(variant: int = 0, exact_pool: bool = False) -> LiftOps:
 def lift_view_sharded(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: torch.Tensor, depth_local: torch.Tensor,
                       fmap_local: torch.Tensor, sp_ids: torch.Tensor, n_superpoints: int, *, stride: float,
                       tau: float = 0.05, z_near: float = 0.1, exchange: str = "allreduce", gather_feats: bool = False,
-                      group=None, ops: Optional[LiftOps] = None):
+                      group=None, ops: Optional[LiftOps] = None, world: Optional[int] = None):
     """Every rank passes the full point set and ITS OWN views. Returns a dict:
     ``sp_feat`` [S,C] (identical on all ranks), ``count`` [N] (global), and
     ``feat`` [N,C] (allreduce / gather_feats) or ``feat_shard`` + ``rows=(begin,end)`` (reduce_scatter)."""
     if ops is None:
         ops = cuda_ops()
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world is None:  # (world=1: this rank holds all the views although a process group exists)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() and world > 1 else 0
     n = xyz.shape[0]
     plan = ops.plan(sp_ids, n_superpoints, xyz)
     part_sum, part_cnt = ops.lift_partial(xyz, K_local, w2c_local, depth_local, fmap_local, stride, tau, z_near, plan)
@@ -188,53 +189,91 @@ class PeerStage:
 def lift_view_sharded_p2p(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: torch.Tensor, depth_local: torch.Tensor,
                           fmap_local: torch.Tensor, sp_ids: torch.Tensor, n_superpoints: int, stage: PeerStage, *,
                           stride: Optional[float] = None, tau: float = 0.05, z_near: float = 0.1, step: int = 0,
-                          variant: int = 0, group=None):
+                          variant: int = 0, group=None, marks: Optional[list] = None, cache: Optional[dict] = None):
     """View-sharded lifting with the exchange FUSED into the gather kernel (CUDA + NVLink peer memory).
 
     Every rank lifts its own views for all points; the gather kernel stores each finished partial row straight into
     the staging buffer of the rank that owns the row's processing position (peer store over NVLink, overlapped with
     the rest of the gather). A one-element all_reduce is the only barrier; then each rank sums its staged rows in
-    rank order, divides by the global count and pools its position shard. No collective moves feature rows.
+    rank order, divides by the global count and pools its position shard -- the positions are superpoint-sorted, so
+    the shard's segments are the plan's segment offsets clipped to the shard (no second sort) -- and ONE all_reduce
+    of [superpoint sums | superpoint sizes] finishes the pooling. No collective moves feature rows.
 
     Returns ``feat_shard`` [rows,C] for processing positions ``rows=(begin,end)`` (point ids ``pids``),
     ``count_shard`` [rows] and ``sp_feat`` [S,C] (identical on all ranks). ``step`` selects the staging buffer
-    (consecutive scenes must alternate)."""
+    (consecutive scenes must alternate). ``cache``: a dict the caller keeps between scenes of the same shape; the
+    workspace and the output buffers then live in it instead of being allocated per scene (results of a scene are
+    overwritten by the scene after next)."""
     from . import ops
     world, rank = stage.world, stage.rank
-    n, c = xyz.shape[0], fmap_local.shape[3]
+    n, c, s = xyz.shape[0], fmap_local.shape[3], int(n_superpoints)
+    dev = xyz.device
     if stage.rows * world < n or stage.c != c:
         raise ValueError("PeerStage is too small for this scene")
+
+    def mark(name):  # bench only: CUDA events between the stages
+        if marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+
     b = step % stage.n_buffers
-    # plan first: the projection kernel is several times faster on the plan's spatially sorted order (neighbouring
-    # lanes read neighbouring depth pixels) than it gains from running concurrently with the plan (measured, cfg4s)
-    plan = ops.sp_sort(sp_ids, n_superpoints, xyz=xyz)
-    ops.lift_push(xyz, K_local, w2c_local, depth_local, fmap_local, stride, plan, n_ranks=world, src_rank=rank,
-                  rows_per_rank=stage.rows, peer_sum=stage.sum_ptrs[b], peer_count=stage.cnt_ptrs[b], tau=tau,
-                  z_near=z_near, variant=variant)
-    token = torch.zeros(1, device=xyz.device)
-    dist.all_reduce(token, group=group)  # barrier on the stream: every rank's gather (and its peer stores) is complete
     begin = min(rank * stage.rows, n)
     end = min(begin + stage.rows, n)
-    feat_shard, cnt_shard = ops.push_reduce(stage.sum_ptrs[b][rank], stage.cnt_ptrs[b][rank], world, stage.rows,
-                                            end - begin, c, xyz.device)
-    # positions are superpoint-sorted: pool the local rows, turn means back into sums, reduce the tiny [S,C]
-    pids = plan.order[begin:end]
-    local_ids = sp_ids[pids.long()].contiguous()
-    local_plan = ops.sp_sort(local_ids, n_superpoints)
-    s = n_superpoints
-    sizes = (local_plan.seg_offsets[1:s + 1] - local_plan.seg_offsets[:s]).to(torch.float32)
-    sp_sum = ops.sp_mean(feat_shard, local_plan, exact=False) * sizes[:, None]
-    dist.all_reduce(sp_sum, group=group)
-    dist.all_reduce(sizes, group=group)
-    return {"feat_shard": feat_shard, "count_shard": cnt_shard, "rows": (begin, end), "pids": pids,
-            "sp_feat": sp_sum / sizes.clamp(min=1)[:, None]}
+    rows = end - begin
+    key = (n, c, s, rows, K_local.shape[0], dev)
+    bufs = cache.get("bufs") if cache is not None else None
+    if bufs is None or bufs["key"] != key:
+        extra = (s + c - 1) // c  # the superpoint sizes ride in `extra` trailing rows of the [S,C] all_reduce buffer
+        bufs = {"key": key, "ws": None, "token": torch.zeros(1, device=dev),
+                "feat": [torch.empty(rows, c, dtype=torch.float32, device=dev) for _ in range(2)],
+                "cnt": [torch.empty(rows, dtype=torch.int32, device=dev) for _ in range(2)],
+                "sp": [torch.empty(s + extra, c, dtype=torch.float32, device=dev) for _ in range(2)],
+                "ident": torch.arange(rows, dtype=torch.int32, device=dev)}
+        ws_bytes = int(ops._lib.load().sd3d_lift_workspace_bytes(n, K_local.shape[0], c, 0))
+        bufs["ws"] = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        if cache is not None:
+            cache["bufs"] = bufs
+    mark("start")
+    # plan first: the projection kernel is several times faster on the plan's spatially sorted order (neighbouring
+    # lanes read neighbouring depth pixels) than it gains from running concurrently with the plan (measured, cfg4s)
+    plan = ops.sp_sort(sp_ids, s, xyz=xyz)
+    mark("plan")
+    ops.lift_push(xyz, K_local, w2c_local, depth_local, fmap_local, stride, plan, n_ranks=world, src_rank=rank,
+                  rows_per_rank=stage.rows, peer_sum=stage.sum_ptrs[b], peer_count=stage.cnt_ptrs[b], tau=tau,
+                  z_near=z_near, variant=variant, ws=bufs["ws"])
+    mark("project+gather+push")
+    dist.all_reduce(bufs["token"], group=group)  # barrier on the stream: every rank's gather (and its peer stores) is complete
+    mark("barrier")
+    feat_shard, cnt_shard = ops.push_reduce(stage.sum_ptrs[b][rank], stage.cnt_ptrs[b][rank], world, stage.rows, rows, c,
+                                            dev, out=(bufs["feat"][b], bufs["cnt"][b]))
+    mark("reduce")
+    # the shard is a contiguous range of superpoint-sorted positions: its segments are the plan's, clipped
+    local_offsets = (plan.seg_offsets - begin).clamp_(0, rows)
+    local_plan = ops.SuperpointPlan(bufs["ident"], bufs["ident"], local_offsets, plan.task_offsets, plan.task_seg, rows, s,
+                                    plan.run, plan.max_tasks)
+    sp_buf = bufs["sp"][b]
+    ops.sp_mean(feat_shard, local_plan, exact=True, out=sp_buf[:s])
+    sizes = (local_offsets[1:s + 1] - local_offsets[:s]).to(torch.float32)
+    sp_buf[:s].mul_(sizes[:, None])            # means back to sums
+    sp_buf[s:].view(-1)[:s].copy_(sizes)
+    mark("pool")
+    dist.all_reduce(sp_buf, group=group)
+    total = sp_buf[s:].view(-1)[:s]
+    sp_feat = sp_buf[:s] / total.clamp(min=1)[:, None]
+    mark("allreduce[S,C]")
+    return {"feat_shard": feat_shard, "count_shard": cnt_shard, "rows": (begin, end), "pids": plan.order[begin:end],
+            "sp_feat": sp_feat}
 
 
-def bench_viewshard(args, rank: int, world: int, dev: torch.device):
-    from bench import WORKLOADS, ClockSampler, algorithmic_bytes, measured_peak_hbm
+def measure_viewshard(wl: dict, exchange: str, steps: int, warmup: int, rank: int, world: int, dev: torch.device,
+                      variant: int = 0, stage_times: bool = False):
+    """Times `steps` view-sharded lifts of one scene of workload `wl` on `world` ranks (world == 1: the whole scene
+    on this rank, no exchange). Every rank builds the same scene and keeps its contiguous view range. Device time
+    with CUDA events, max over ranks. Returns (ms_per_step, n_superpoints, clocks)."""
+    from bench import ClockSampler
     from .synth import make_scene
 
-    wl = WORKLOADS[args.workload]
     sc = make_scene(seed=1235, fmap_device=dev, **wl)  # identical on every rank (same seeds)
     vb, ve = shard_range(wl["n_views"], world, rank)
     d = {k: getattr(sc, k).to(dev) for k in ("xyz", "sp_ids")}
@@ -244,25 +283,23 @@ def bench_viewshard(args, rank: int, world: int, dev: torch.device):
     fmap_l = sc.fmap[vb:ve].contiguous()
     del sc.fmap
     torch.cuda.empty_cache()
-    ops = cuda_ops(variant=args.variant)
+    ops = cuda_ops(variant=variant)
     stage = None
-    if args.exchange == "p2p" and world > 1:
-        rows = (wl["n_points"] + world - 1) // world
-        stage = PeerStage(rows, wl["channels"], dev)
+    if exchange == "p2p" and world > 1:
+        stage = PeerStage((wl["n_points"] + world - 1) // world, wl["channels"], dev)
     step_no = [0]
+    cache = {}
 
-    def step():
+    def step(marks=None):
         if stage is not None:
             step_no[0] += 1
             return lift_view_sharded_p2p(d["xyz"], K_l, w2c_l, depth_l, fmap_l, d["sp_ids"], sc.n_superpoints, stage,
-                                         stride=sc.stride, step=step_no[0], variant=args.variant)
-        if args.exchange == "p2p":  # one rank: nothing to exchange
-            return lift_view_sharded(d["xyz"], K_l, w2c_l, depth_l, fmap_l, d["sp_ids"], sc.n_superpoints,
-                                     stride=sc.stride, exchange="allreduce", ops=ops)
+                                         stride=sc.stride, step=step_no[0], variant=variant, cache=cache, marks=marks)
+        ex = "allreduce" if exchange == "p2p" else exchange  # one rank: nothing to exchange
         return lift_view_sharded(d["xyz"], K_l, w2c_l, depth_l, fmap_l, d["sp_ids"], sc.n_superpoints,
-                                 stride=sc.stride, exchange=args.exchange, ops=ops)
+                                 stride=sc.stride, exchange=ex, ops=ops, world=world)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     torch.cuda.synchronize()
     if world > 1:
@@ -272,22 +309,72 @@ def bench_viewshard(args, rank: int, world: int, dev: torch.device):
     torch.cuda.synchronize()
     sampler.start()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
-    ms = e0.elapsed_time(e1) / args.steps
+    ms = e0.elapsed_time(e1) / steps
+    if stage is not None and stage_times:
+        acc = {}
+        for _ in range(10):
+            marks = []
+            step(marks)
+            torch.cuda.synchronize()
+            for (_, a), (name, b2) in zip(marks[:-1], marks[1:]):
+                acc[name] = acc.get(name, 0.0) + a.elapsed_time(b2) / 10
+        print(f"[rank {rank}] stage ms: " + "  ".join(f"{k}={v:.3f}" for k, v in acc.items()), file=__import__("sys").stderr,
+              flush=True)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
+    if stage is not None:
+        stage.close()
+    n_sp = sc.n_superpoints
+    del sc, d, K_l, w2c_l, depth_l, fmap_l, cache
+    torch.cuda.empty_cache()
+    return ms, n_sp, clocks
+
+
+def viewshard_report(wl: dict, workload: str, exchange: str, steps: int, warmup: int, rank: int, world: int,
+                     dev: torch.device, variant: int = 0) -> Optional[dict]:
+    """The north-star multi-GPU split as an object for bench.py's JSON line: one scene of `workload` with its views
+    sharded over all `world` ranks, and -- measured in the same run, on rank 0 alone -- the same scene on one GPU.
+    speedup = ms_1gpu / ms_per_step. Returns the object on rank 0, None elsewhere."""
+    ms_n = None
+    if world > 1:
+        ms_n, n_sp, _ = measure_viewshard(wl, exchange, steps, warmup, rank, world, dev, variant)
+    ms_1 = n_sp1 = None
+    if rank == 0:
+        ms_1, n_sp1, _ = measure_viewshard(wl, "allreduce", max(steps // 2, 5), warmup, 0, 1, dev, variant)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        return None
+    out = {"workload": workload, "n_points": wl["n_points"], "n_views": wl["n_views"], "n_superpoints": n_sp1,
+           "ms_1gpu": ms_1, "scenes_per_s_1gpu": 1e3 / ms_1}
+    if world > 1:
+        out.update({"n_gpus": world, "exchange": exchange, "ms_per_step": ms_n, "scenes_per_s": 1e3 / ms_n,
+                    "speedup_vs_1gpu": ms_1 / ms_n, "scaling": "strong",
+                    "note": "views of ONE scene sharded over the ranks; p2p = partial rows stored by the gather kernel "
+                            "straight into the owner rank's staging buffer over NVLink (sd3d_lift_push), one barrier, "
+                            "owner-side reduce + pooling, one all_reduce of [S,C+1]"})
+    return out
+
+
+def bench_viewshard(args, rank: int, world: int, dev: torch.device):
+    from bench import WORKLOADS, algorithmic_bytes, measured_peak_hbm
+
+    wl = WORKLOADS[args.workload]
+    ms, n_sp, clocks = measure_viewshard(wl, args.exchange, args.steps, args.warmup, rank, world, dev, args.variant,
+                                         stage_times=bool(os.environ.get("SD3D_STAGE_TIMES")))
     if rank == 0:
         n, v = wl["n_points"], wl["n_views"]
         hf, wf, c = wl["hd"] // wl["stride"], wl["wd"] // wl["stride"], wl["channels"]
-        _, b_path = algorithmic_bytes(n, v, wl["hd"], wl["wd"], hf, wf, c, sc.n_superpoints)
+        _, b_path = algorithmic_bytes(n, v, wl["hd"], wl["wd"], hf, wf, c, n_sp)
         peak, peak_src = measured_peak_hbm()
         value = 1e3 / ms
         line = {
@@ -295,7 +382,7 @@ def bench_viewshard(args, rank: int, world: int, dev: torch.device):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "n_points": n, "n_views": v, "fmap": [hf, wf, c],
-                       "n_superpoints": sc.n_superpoints, "parallelism": f"views sharded over {world} ranks",
+                       "n_superpoints": n_sp, "parallelism": f"views sharded over {world} ranks",
                        "exchange": args.exchange if world > 1 else "none",
                        "l2": "per-rank inputs (maps+depth) exceed the 126 MB L2; no flush"},
             "points_per_s": value * n,
@@ -303,11 +390,9 @@ def bench_viewshard(args, rank: int, world: int, dev: torch.device):
                          "peak": peak * world, "unit": "GB/s", "frac": b_path / (ms * 1e-3) / 1e9 / (peak * world),
                          "traffic": None, "peak_source": peak_src},
             "clocks": clocks,
-            # own kernels per scene: plan 3 + projection + gather + finalize / push-reduce + pooling (2-4)
-            "gpu_launches": (10 if world > 1 else 8) * args.steps,
+            # own kernels per scene: plan 3 + projection + gather + finalize / push-reduce + pooling
+            "gpu_launches": (7 if world > 1 else 8) * args.steps,
         }
         print(json.dumps(line), flush=True)
-    if stage is not None:
-        stage.close()
     if world > 1:
         dist.destroy_process_group()

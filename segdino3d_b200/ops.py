@@ -400,7 +400,7 @@ def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Ten
 def lift_push(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Tensor, fmap: torch.Tensor,
               stride: Optional[float], plan: SuperpointPlan, *, n_ranks: int, src_rank: int, rows_per_rank: int,
               peer_sum: Sequence[int], peer_count: Sequence[int], tau: float = TAU_DEFAULT,
-              z_near: float = Z_NEAR_DEFAULT, variant: int = 0) -> None:
+              z_near: float = Z_NEAR_DEFAULT, variant: int = 0, ws: Optional[torch.Tensor] = None) -> None:
     """View-sharded lifting with the exchange fused into the gather (``sd3d_lift_push``): this rank lifts ITS views
     for all points and stores every un-normalised row + visible count directly into the staging buffers of the rank
     owning the row's processing position (``peer_sum[r]`` / ``peer_count[r]``: device addresses, valid on this
@@ -419,7 +419,8 @@ def lift_push(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torc
     cnts = (ctypes.c_void_p * n_ranks)(*[int(a) for a in peer_count])
     with torch.cuda.device(xyz.device):
         ws_bytes = int(lib.sd3d_lift_workspace_bytes(n, v, c, 0))
-        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xyz.device)
+        if ws is None or ws.numel() < ws_bytes:  # callers that lift scene after scene keep the workspace
+            ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=xyz.device)
 
         # the plan comes first on purpose: the projection kernel is several times faster on the plan's spatially
         # sorted order than it gains from running concurrently with the plan (measured on cfg4s)
@@ -430,13 +431,16 @@ def lift_push(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torc
 
 
 def push_reduce(stage_sum: int, stage_count: int, n_ranks: int, rows_per_rank: int, rows: int, channels: int,
-                device: torch.device) -> Tuple[torch.Tensor, torch.Tensor]:
+                device: torch.device, out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Second half of ``lift_push`` on the owning rank: sums the ``n_ranks`` staged partial rows of each owned
     position in ascending rank order and divides by max(total count, 1). Returns (feat [rows,C], count [rows])."""
     lib = _lib.load()
     with torch.cuda.device(device):
-        feat = torch.empty(rows, channels, dtype=torch.float32, device=device)
-        count = torch.empty(rows, dtype=torch.int32, device=device)
+        if out is not None:
+            feat, count = out
+        else:
+            feat = torch.empty(rows, channels, dtype=torch.float32, device=device)
+            count = torch.empty(rows, dtype=torch.int32, device=device)
         check(lib.sd3d_push_reduce(int(stage_sum), int(stage_count), int(n_ranks), int(rows_per_rank), int(rows),
                                    int(channels), _ptr(feat), _ptr(count), _stream()), "sd3d_push_reduce")
     return feat, count
@@ -495,19 +499,68 @@ def _side_stream(dev: torch.device) -> torch.cuda.Stream:
     return st
 
 
+class LiftPoolBuffers:
+    """Outputs, plan arrays and workspace of ``lift_and_pool`` for scenes of one shape, allocated once and reused
+    (``buffers=`` argument): the host side of a step is then one C call with no allocation. Results of a step are
+    overwritten by the next step that uses the same buffers (copy out, or use one set per scene in flight)."""
+
+    def __init__(self, n: int, n_views: int, channels: int, n_superpoints: int, run: int, device: torch.device):
+        lib = _lib.load()
+        self.key = (int(n), int(n_views), int(channels), int(n_superpoints), int(run), torch.device(device))
+        self.max_tasks = int(lib.sd3d_sp_max_tasks(n, n_superpoints, run))
+        with torch.cuda.device(device):
+            i32 = dict(dtype=torch.int32, device=device)
+            self.feat = torch.empty(n, channels, dtype=torch.float32, device=device)
+            self.count = torch.empty(n, **i32)
+            self.sp_out = torch.empty(n_superpoints, channels, dtype=torch.float32, device=device)
+            self.perm, self.order = torch.empty(n, **i32), torch.empty(n, **i32)
+            self.seg_offsets, self.task_offsets = torch.empty(n_superpoints + 2, **i32), torch.empty(n_superpoints + 2, **i32)
+            self.task_seg = torch.empty(max(self.max_tasks, 1), **i32)
+            self.ws_bytes = int(lib.sd3d_lift_and_pool_workspace_bytes(n, n_superpoints, n_views, channels, run))
+            self.ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=device)
+        self.plan = SuperpointPlan(self.perm, self.order, self.seg_offsets, self.task_offsets, self.task_seg, int(n),
+                                   int(n_superpoints), int(run), self.max_tasks)
+
+
 def lift_and_pool(xyz, K, pose_w2c, depth, fmap, sp_ids: torch.Tensor, n_superpoints: Optional[int] = None, *,
                   stride: Optional[float] = None, tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT,
                   run: int = DEFAULT_RUN, variant: int = 0, overlap: bool = True,
-                  events: Optional[Tuple[torch.cuda.Event, torch.cuda.Event]] = None):
+                  events: Optional[Tuple[torch.cuda.Event, torch.cuda.Event]] = None,
+                  buffers: Optional[LiftPoolBuffers] = None, refine_cell: float = 0.08):
     """The whole hot path for one scene: plan (sort by superpoint + spatial refinement + run table), projection,
     gather + mean + run partials, ordered combine. Returns (points_2dfeats [N,C], count [N], sp_feats [S,C], plan).
 
-    ``overlap``: the projection kernel needs no plan, so it is launched on a side stream and runs concurrently
-    with the (latency-bound) plan kernels; the gather waits for both."""
+    Default: ONE C call (``sd3d_lift_and_pool``) enqueues all kernels; the projection runs on a library-owned side
+    stream concurrently with the plan kernels. ``buffers`` (``LiftPoolBuffers``) makes the call allocation-free.
+    ``overlap=False`` or ``events`` (bench: brackets the gather) take the step-by-step path through the separate
+    entries, same kernels and results."""
     _need_cuda("sp_ids", sp_ids)
     n = xyz.shape[0]
     if n_superpoints is None:
         n_superpoints = int(sp_ids.max().item()) + 1 if n > 0 else 0
+    if events is None and overlap:
+        _check_lift_inputs(xyz, K, pose_w2c, depth, fmap)
+        v, hd, wd = K.shape[0], depth.shape[1], depth.shape[2]
+        hf, wf, c = fmap.shape[1], fmap.shape[2], fmap.shape[3]
+        key = (int(n), int(v), int(c), int(n_superpoints), int(run), xyz.device)
+        if buffers is None:
+            buffers = LiftPoolBuffers(n, v, c, n_superpoints, run, xyz.device)
+        elif buffers.key != key:
+            raise ValueError(f"buffers were made for {buffers.key}, this scene is {key}")
+        if sp_ids.dtype != torch.int64 or sp_ids.numel() != n:
+            raise ValueError("sp_ids must be int64 [N]")
+        B = buffers
+        xyz, K, pose_w2c, depth, fmap, sp_ids = (t if t.is_contiguous() else t.contiguous()
+                                                 for t in (xyz, K, pose_w2c, depth, fmap, sp_ids))
+        with torch.cuda.device(xyz.device):
+            check(_lib.load().sd3d_lift_and_pool(
+                xyz.data_ptr(), n, K.data_ptr(), pose_w2c.data_ptr(), v, depth.data_ptr(), _DEPTH_CODE[depth.dtype], hd, wd,
+                fmap.data_ptr(), _FMAP_CODE[fmap.dtype], hf, wf, c, float(wd / wf if stride is None else stride),
+                float(tau), float(z_near), sp_ids.data_ptr(), int(n_superpoints), int(run), float(refine_cell),
+                B.perm.data_ptr(), B.order.data_ptr(), B.seg_offsets.data_ptr(), B.task_offsets.data_ptr(),
+                B.task_seg.data_ptr(), B.max_tasks, B.feat.data_ptr(), B.count.data_ptr(), B.sp_out.data_ptr(),
+                B.ws.data_ptr(), B.ws_bytes, int(variant), torch.cuda.current_stream().cuda_stream), "sd3d_lift_and_pool")
+        return B.feat, B.count, B.sp_out, B.plan
     max_tasks = int(_lib.load().sd3d_sp_max_tasks(n, int(n_superpoints), run))
     L = _LiftLaunch(xyz, K, pose_w2c, depth, fmap, stride, tau, z_near, None, True, True, False, None, variant,
                     n_superpoints, max_tasks, run)

@@ -35,6 +35,7 @@ class _Slot:
         self.ev_d2h = torch.cuda.Event()
         self.busy = False
         self.meta = None
+        self.buffers = None          # ops.LiftPoolBuffers of the scene shape this slot last held
 
 
 class ScenePipeline:
@@ -80,9 +81,12 @@ class ScenePipeline:
         with torch.cuda.stream(self.s_comp):
             self.s_comp.wait_event(slot.ev_h2d)
             self.s_comp.wait_event(slot.ev_d2h)  # the previous outputs of this slot have left the device
+            key = (d["xyz"].shape[0], d["K"].shape[0], d["fmap"].shape[3], n_sp, self.run_len, self.device)
+            if slot.buffers is None or slot.buffers.key != key:  # outputs + workspace live with the slot
+                slot.buffers = ops.LiftPoolBuffers(*key)
             feat, count, sp, plan = ops.lift_and_pool(d["xyz"], d["K"], d["w2c"], d["depth"], d["fmap"], d["sp_ids"], n_sp,
                                                       stride=stride, tau=self.tau, z_near=self.z_near, run=self.run_len,
-                                                      variant=self.variant, overlap=True)
+                                                      variant=self.variant, overlap=True, buffers=slot.buffers)
             slot.out_dev = (feat, count, sp, plan)
             slot.ev_comp.record(self.s_comp)
 

@@ -420,6 +420,35 @@ def test_fused_lift_pool(adversarial):
     assert rel_row_err(sd.sp_mean(raw["feat"], plan, exact=False, point_count=raw["count"]), sp_o) <= 1e-5
 
 
+def test_lift_and_pool_one_call_with_persistent_buffers():
+    """sd3d_lift_and_pool (one C call: plan, projection on a side stream, gather, combine) with a LiftPoolBuffers
+    reused across scenes == the step-by-step entries == the oracle."""
+    scs = [make_scene(n_points=20_000, n_views=10, hd=120, wd=160, stride=8, channels=256, seed=50 + i, sp_target=90)
+           for i in range(2)]
+    bufs = {}
+    for rep in range(2):
+        for sc in scs:
+            a, c, _, _ = c_ref.lift_ref(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride, want_maps=False)
+            feat_o = lo.lift_finalize_oracle(a, c)
+            sp_o = so.scatter_mean_oracle(feat_o, sc.sp_ids, dim=0)
+            d = sc.to(DEV)
+            b = bufs.setdefault(sc.n_superpoints, sd.LiftPoolBuffers(20_000, 10, 256, sc.n_superpoints, 32, torch.device(DEV)))
+            feat, cnt, sp, plan = sd.lift_and_pool(d.xyz, d.K, d.w2c, d.depth, d.fmap, d.sp_ids, sc.n_superpoints, buffers=b)
+            assert feat.data_ptr() == b.feat.data_ptr()
+            assert torch.equal(cnt.cpu(), c) and torch.equal(feat.cpu(), feat_o) and rel_row_err(sp, sp_o) <= 1e-5
+            perm, offs = so.sp_sort_oracle(sc.sp_ids, sc.n_superpoints)
+            assert torch.equal(plan.perm.cpu(), perm) and torch.equal(plan.seg_offsets[: sc.n_superpoints + 1].cpu(), offs)
+            f2, c2, s2, _ = sd.lift_and_pool(d.xyz, d.K, d.w2c, d.depth, d.fmap, d.sp_ids, sc.n_superpoints, overlap=False)
+            assert torch.equal(f2, feat) and torch.equal(c2, cnt) and torch.equal(s2, sp)
+            f3, c3, s3, _ = sd.lift_and_pool(d.xyz, d.K, d.w2c, d.depth, d.fmap, d.sp_ids, sc.n_superpoints,
+                                             variant=32768, buffers=b)
+            assert torch.equal(f3.cpu(), feat_o) and torch.equal(c3.cpu(), c) and rel_row_err(s3, sp_o) <= 1e-5
+    with pytest.raises(ValueError):
+        sd.lift_and_pool(d.xyz[:100], d.K, d.w2c, d.depth, d.fmap, d.sp_ids[:100], sc.n_superpoints, buffers=b)
+    e = sd.lift_and_pool(d.xyz[:0], d.K, d.w2c, d.depth, d.fmap, d.sp_ids[:0], 7)
+    assert e[0].shape == (0, 256) and e[2].shape == (7, 256) and float(e[2].abs().sum()) == 0.0
+
+
 def test_full_size_scene_cfg2():
     """BASELINE configs[1]: 100k points, 40 views 640x480, 256-d stride-8 maps, ~500 superpoints."""
     sc = make_scene(seed=1235)
