@@ -122,6 +122,9 @@ int sd3d_sp_mean(const float* src, const int32_t* perm, const int32_t* seg_offse
  *   needs `order`) also plans the stages; after a projection WITHOUT order, bit 9 (512) runs a stand-alone stage
  *   planner before the gather; bit 12 (4096) = that planner only, bit 13 (8192) = gather only, stages planned.
  *   Bits 2 / 3 then mean: two samples in flight per consumer warp / 4 consumer warps x 8 points instead of 8 x 4.
+ *   bits 16..23 = k (0..8): nearest-view sampling (the "Nearest View Sampling" box of the paper's overview figure,
+ *   assets/overview.png; no code in the reference): of the views that see a point only the k with the smallest camera
+ *   depth zc are summed and counted (ties to the lower view index); pix_idx / vis still report plain visibility.
  * --------------------------------------------------------------------------------------------- */
 size_t sd3d_lift_workspace_bytes(int64_t N, int n_views, int C, int64_t max_tasks);
 int sd3d_lift(const float* xyz, int64_t N, const float* K4, const float* w2c, int V, int view_begin, int view_end,
@@ -211,6 +214,15 @@ int sd3d_mask_logits(const float* q, const float* mf, int n, int S, int d, int p
  * pointnum[K] int32 (fully overwritten). Ids outside [0,S) expand to 0. */
 int sd3d_sp_expand_mask(const float* mask_sig, const int64_t* superpoints, int K, int64_t S, int64_t N, float thr,
                         uint8_t* out, int32_t* pointnum, void* stream);
+
+/* Superpoint-level ground truth, one pass: out[s,k] = (mean over the points of superpoint s of [labels == k]) > 0.5
+ *   == scatter_mean(F.one_hot(labels)[:, :K].float(), super_point_masks, dim=0) > 0.5
+ *   segdino3d/datasets/dataset/scannet200.py:243-253 ; scannet.py:204-211 (instance and semantic variants).
+ * labels[N] int64 (values outside [0,K) -- the background the reference drops -- vote for nobody), perm / seg_offsets
+ * from sd3d_sp_sort of the superpoint ids, out[S,K] u8 fully overwritten. background_if_none != 0: a row without a
+ * winner gets its LAST column set (scannet200.py:251). Integer counting: 2 * count > size, exact. */
+int sd3d_sp_label_vote(const int64_t* labels, const int32_t* perm, const int32_t* seg_offsets, int64_t N, int64_t S,
+                       int K, int background_if_none, uint8_t* out, void* stream);
 
 /* Gradient of scatter_mean(src, idx, dim=0) w.r.t. src: grad_src[p,:] = grad_out[idx[p],:] / max(|idx[p]|,1)
  *   (the pooling runs under autograd in training: engine/train_engine_3d.py:99-105, spconvunet.py:390).

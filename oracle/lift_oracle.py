@@ -38,7 +38,7 @@ def _depth_to_f32(depth_v: torch.Tensor) -> torch.Tensor:
 
 
 def project_view(xyz: torch.Tensor, K_v: torch.Tensor, w2c_v: torch.Tensor, depth_v: torch.Tensor,
-                 tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT):
+                 tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT, return_depth: bool = False):
     """Step a-1 for one view. Returns (idx[int64, M] of visible points, u[M], w[M], pix[int32, M]).
 
     Appendix A lines `xc = ...` .. `pix_idx[v,p] = wi*Wd + ui`.
@@ -64,7 +64,25 @@ def project_view(xyz: torch.Tensor, K_v: torch.Tensor, w2c_v: torch.Tensor, dept
     pix = wi * wd + ui
     d = _depth_to_f32(depth_v.reshape(-1)[pix])
     ok = (d > 0) & ((d - zc).abs() <= torch.tensor(tau, dtype=torch.float32))
+    if return_depth:
+        return idx[ok], u[ok], w[ok], pix[ok].to(torch.int32), zc[ok]
     return idx[ok], u[ok], w[ok], pix[ok].to(torch.int32)
+
+
+def nearest_view_selection(xyz, K, w2c, depth, k_views: int, tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT,
+                           views: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """Nearest-view sampling variant (paper overview figure; spec decision of this repo): of the views that
+    see a point, only the ``k_views`` with the smallest camera depth zc count, ties going to the lower view index.
+    Returns the bool selection [V, N] (a subset of vis)."""
+    n, v_total = xyz.shape[0], K.shape[0]
+    zmat = torch.full((v_total, n), float("inf"), dtype=torch.float32)
+    for v in (range(v_total) if views is None else views):
+        idx, _, _, _, zc = project_view(xyz, K[v], w2c[v], depth[v], tau, z_near, return_depth=True)
+        zmat[v, idx] = zc
+    order = torch.sort(zmat, dim=0, stable=True).indices[:k_views]          # [k, N] view indices, nearest first
+    sel = torch.zeros(v_total, n, dtype=torch.bool)
+    sel.scatter_(0, order, torch.ones_like(order, dtype=torch.bool))
+    return sel & torch.isfinite(zmat)
 
 
 def gather_view(fmap_v: torch.Tensor, u: torch.Tensor, w: torch.Tensor, stride: float) -> torch.Tensor:
@@ -101,7 +119,7 @@ def gather_view(fmap_v: torch.Tensor, u: torch.Tensor, w: torch.Tensor, stride: 
 def lift_accumulate_oracle(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Tensor,
                            fmap: torch.Tensor, stride: float, tau: float = TAU_DEFAULT,
                            z_near: float = Z_NEAR_DEFAULT, want_maps: bool = True,
-                           views: Optional[Sequence[int]] = None):
+                           views: Optional[Sequence[int]] = None, k_views: int = 0):
     """Steps a-1..a-3 (accumulate part). Returns (sum[N,C] f32, count[N] i32, pix_idx[V,N] i32, vis[V,N] u8).
 
     ``views`` restricts the ascending view loop to a subset (the multi-GPU view shard of SURVEY 8e);
@@ -114,11 +132,15 @@ def lift_accumulate_oracle(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor
     cnt = torch.zeros(n, dtype=torch.int32)
     pix_idx = torch.full((v_total, n), -1, dtype=torch.int32) if want_maps else None
     vis = torch.zeros((v_total, n), dtype=torch.uint8) if want_maps else None
+    sel = nearest_view_selection(xyz, K, w2c, depth, k_views, tau, z_near, views) if k_views > 0 else None
     for v in (range(v_total) if views is None else views):
         idx, u, w, pix = project_view(xyz, K[v], w2c[v], depth[v], tau, z_near)
-        if want_maps:
+        if want_maps:  # the parity maps report visibility, whatever the view selection
             pix_idx[v, idx] = pix
             vis[v, idx] = 1
+        if sel is not None:  # k_views > 0: only the selected (nearest) views are summed and counted
+            keep = sel[v, idx]
+            idx, u, w = idx[keep], u[keep], w[keep]
         if idx.numel() == 0:
             continue
         cnt[idx] += 1

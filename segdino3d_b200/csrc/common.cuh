@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "../../include/sd3d.h"
 
 namespace sd3d {
@@ -17,6 +19,15 @@ int check_launch(const char* what);
 int num_sms();
 // a library-owned non-blocking side stream of the current device (small pool, round robin; never destroyed); nullptr on error
 cudaStream_t plan_side_stream();
+
+// Per-DEVICE once flag for function attributes (cudaFuncSetAttribute is per device; a process may drive several):
+// returns true the first time it is called on the current device (always true for device ordinals >= 64).
+inline bool first_on_device(std::atomic<uint64_t>* seen) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const uint64_t bit = uint64_t(1) << dev;
+    return (seen->fetch_or(bit) & bit) == 0;
+}
 
 constexpr unsigned kFull = 0xffffffffu;
 

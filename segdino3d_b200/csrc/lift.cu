@@ -29,7 +29,9 @@ namespace sd3d {
 // ---------------------------------------------------------------------------------------------------
 constexpr int kProjThreads = 64;
 constexpr int kProjViews = 4;  // views per round: 4 independent depth reads in flight per lane
+constexpr int kMaxNearest = 8;  // largest k of the nearest-view sampling variant
 
+template <bool NEAREST>
 __global__ void __launch_bounds__(kProjThreads) project_kernel(const LiftParams p, uint32_t* __restrict__ masks,
                                                                int nchunks, int32_t* __restrict__ plan_done,
                                                                int64_t n_done) {
@@ -47,6 +49,14 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(const LiftParams 
     uint32_t* __restrict__ mrow = masks + pid * nchunks;
     int nv = 0;        // visible views so far = slot of the next record
     uint32_t m = 0u;   // mask word being filled
+    // nearest-view sampling (k_views > 0): the k visible views with the smallest camera depth, ties to the lower view
+    float best_z[kMaxNearest];
+    int best_v[kMaxNearest];
+#pragma unroll
+    for (int j = 0; j < kMaxNearest; ++j) {
+        best_z[j] = 0.f;
+        best_v[j] = -1;
+    }
     for (int v0 = p.v_begin; v0 < p.v_end; v0 += kProjViews) {
         float zc[kProjViews], d[kProjViews], us[kProjViews], ws[kProjViews];
         int cand[kProjViews];
@@ -88,6 +98,30 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(const LiftParams 
                     const TapGeom g = tap_geometry(us[t], ws[t], p.stride, p.inv_stride, p.Hf, p.Wf);
                     recs[nv++] = make_record(g, g.ax, g.ay, v, p.Hf, p.Wf);
                     m |= 1u << bit;
+                    if (NEAREST) {  // keep (zc, v) if it is among the k smallest so far: evict the largest (zc, v)
+                        int worst = -1, wv = -2;  // slot to replace; wv = its view (-1: a free slot, always taken)
+                        float wz = 0.f;
+#pragma unroll
+                        for (int j = 0; j < kMaxNearest; ++j) {
+                            if (j < p.k_views && wv != -1) {
+                                if (best_v[j] < 0) {
+                                    worst = j;
+                                    wv = -1;
+                                } else if (worst < 0 || best_z[j] > wz || (best_z[j] == wz && best_v[j] > wv)) {
+                                    worst = j;
+                                    wz = best_z[j];
+                                    wv = best_v[j];
+                                }
+                            }
+                        }
+                        const bool take = wv == -1 || zc[t] < wz;
+#pragma unroll
+                        for (int j = 0; j < kMaxNearest; ++j)
+                            if (j == worst && take) {
+                                best_z[j] = zc[t];
+                                best_v[j] = v;
+                            }
+                    }
                 }
                 if (bit == 31 || v == p.v_end - 1) {
                     mrow[(v - p.v_begin) >> 5] = m;
@@ -95,6 +129,26 @@ __global__ void __launch_bounds__(kProjThreads) project_kernel(const LiftParams 
                 }
             }
         }
+    }
+    if (NEAREST && nv > p.k_views) {
+        // keep only the selected views' records (the i-th set mask bit is the i-th record), still in ascending view order
+        int i = 0, j = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            uint32_t w = mrow[c];
+            while (w) {
+                const int v = p.v_begin + c * 32 + __ffs(w) - 1;
+                w &= w - 1u;
+                bool sel = false;
+#pragma unroll
+                for (int q = 0; q < kMaxNearest; ++q) sel |= best_v[q] == v;
+                if (sel) {
+                    if (j != i) recs[j] = recs[i];
+                    ++j;
+                }
+                ++i;
+            }
+        }
+        nv = j;
     }
     p.nvis[pid] = nv;
 }
@@ -663,6 +717,11 @@ static int lift_impl(const float* xyz, int64_t N, const float* K4, const float* 
     p.nvis = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(masks) + align_up((size_t)N * nchunks * sizeof(uint32_t), 256));
     p.recs = reinterpret_cast<int4*>(reinterpret_cast<uint8_t*>(p.nvis) + align_up((size_t)N * sizeof(int32_t), 256));
     p.n_views = n_views;
+    p.k_views = (variant >> 16) & 0xff;
+    if (p.k_views > kMaxNearest || (p.k_views > 0 && ((variant & 2) || accumulate))) {
+        set_error("sd3d_lift: nearest-view sampling supports k <= %d, the default gather and accumulate = 0", kMaxNearest);
+        return SD3D_ERR_UNSUPPORTED;
+    }
     p.n_peers = 0;
     p.src_rank = 0;
     p.task_rot = 0;
@@ -698,7 +757,7 @@ static int lift_impl(const float* xyz, int64_t N, const float* K4, const float* 
     sp.cap_pix = sp.ring_slots = 0;
     sp.masks = masks;
     sp.nchunks = nchunks;
-    const bool staged = (variant & 32768) != 0 && (variant & 2) == 0 && staged_supported(p, fmap_dtype, n_views);
+    const bool staged = (variant & 32768) != 0 && (variant & 2) == 0 && p.k_views == 0 && staged_supported(p, fmap_dtype, n_views);
     if (staged) {
         // variant bit 15: tap rows staged in shared memory by the bulk-copy engine (lift_staged.cu); the projection
         // kernel of that path also plans the stages
@@ -710,9 +769,11 @@ static int lift_impl(const float* xyz, int64_t N, const float* K4, const float* 
         }
         return check_launch("sd3d_lift(staged)");
     }
-    if (do_project && nchunks > 0)
-        project_kernel<<<(unsigned)ceil_div64(N, kProjThreads), kProjThreads, 0, stream>>>(p, masks, nchunks, sp.done,
-                                                                                           sp.n_done);
+    if (do_project && nchunks > 0) {
+        const unsigned pgrid = (unsigned)ceil_div64(N, kProjThreads);
+        if (p.k_views > 0) project_kernel<true><<<pgrid, kProjThreads, 0, stream>>>(p, masks, nchunks, sp.done, sp.n_done);
+        else project_kernel<false><<<pgrid, kProjThreads, 0, stream>>>(p, masks, nchunks, sp.done, sp.n_done);
+    }
     int rc;
     if (!do_gather) return check_launch("sd3d_lift(project)");
     switch (fmap_dtype) {

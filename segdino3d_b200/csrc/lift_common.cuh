@@ -50,6 +50,7 @@ struct LiftParams {
     int64_t rows_per_rank;
     float* peer_out[kMaxPeers];
     int32_t* peer_cnt[kMaxPeers];
+    int k_views;      // > 0: nearest-view sampling -- only the k_views visible views with the smallest camera depth count
     int4* recs;       // [N][n_views]; only the first nvis[pid] entries of a row are written
     int32_t* nvis;    // [N]
     int n_views;

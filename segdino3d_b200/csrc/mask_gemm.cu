@@ -377,18 +377,18 @@ extern "C" int sd3d_mask_logits(const float* q, const float* mf, int n, int S, i
         }
         const int stages = d <= 256 ? 2 : 1;  // two B / TMEM stages fit beside a 128 x 256 bf16 A tile
         const size_t smem = (size_t)(d / kTcKBlock) * (kTcBM + stages * kTcBN) * 128 + 1024;
-        static bool attr_set = false;  // idempotent attribute; benign race
-        if (!attr_set) {
+        static std::atomic<uint64_t> attr_set{0};  // per-device flag (the attribute is per device)
+        if (first_on_device(&attr_set)) {
             cudaError_t e = cudaFuncSetAttribute(mask_logits_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)(512 / kTcKBlock * (kTcBM + kTcBN) * 128 + 1024));
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(mask_logits_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(256 / kTcKBlock * (kTcBM + 2 * kTcBN) * 128 + 1024));
             if (e != cudaSuccess) {
+                attr_set.store(0);
                 set_error("sd3d_mask_logits: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
                 return SD3D_ERR_CUDA;
             }
-            attr_set = true;
         }
         // N tiles per CTA: keep >= ~2 CTAs per SM in the grid, at most kTcMaxTiles per CTA
         const int n_tiles = (S + kTcBN - 1) / kTcBN, m_blocks = (n + kTcBM - 1) / kTcBM;

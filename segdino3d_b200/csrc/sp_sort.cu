@@ -630,21 +630,21 @@ static size_t sort_ws_layout(int64_t N, int64_t S, void* ws, SortWs* out) {
     return off + 256;
 }
 
-static int set_smem_attr_once(const void* fn, int bytes, bool* done, const char* what) {
-    if (*done) return SD3D_OK;
+static int set_smem_attr_once(const void* fn, int bytes, std::atomic<uint64_t>* done, const char* what) {
+    if (!first_on_device(done)) return SD3D_OK;  // the attribute is per device
     const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) {
+        done->store(0);
         set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
         return SD3D_ERR_CUDA;
     }
-    *done = true;
     return SD3D_OK;
 }
 
 // sort (+ optional cell keys); the shared body of sd3d_sp_sort and sd3d_sp_plan
 static int run_sort(const int64_t* idx, const float* xyz, float inv_cell, int64_t N, int64_t S, int32_t* perm,
                     int32_t* seg_offsets, const SortWs& w, cudaStream_t stream) {
-    static bool scan_attr = false;
+    static std::atomic<uint64_t> scan_attr{0};
     int rc = set_smem_attr_once(reinterpret_cast<const void*>(radix_scan_kernel), kScanCap * (int)sizeof(int32_t),
                                 &scan_attr, "sd3d_sp_sort");
     if (rc != SD3D_OK) return rc;
@@ -681,7 +681,7 @@ static int run_sort(const int64_t* idx, const float* xyz, float inv_cell, int64_
                             (void*)&xyz, (void*)&inv_cell, (void*)&cell_out, (void*)&seg_};
             const void* fn = first ? reinterpret_cast<const void*>(radix_pass_fused_kernel<true>)
                                    : reinterpret_cast<const void*>(radix_pass_fused_kernel<false>);
-            static bool attr_t = false, attr_f = false;
+            static std::atomic<uint64_t> attr_t{0}, attr_f{0};
             rc = set_smem_attr_once(fn, kScanCap * (int)sizeof(int32_t), first ? &attr_t : &attr_f, "sd3d_sp_sort");
             if (rc != SD3D_OK) return rc;
             const cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(g.nb), dim3(kSortThreads), args, sm_fused, stream);
@@ -725,7 +725,7 @@ static int run_tasks(const int32_t* seg_offsets, const int32_t* perm, const floa
         int n2 = 1;
         while (n2 < nseg) n2 <<= 1;
         smem = (size_t)(nseg <= kMaxRankedSegs ? 2 * kMaxRankedSegs : n2) * sizeof(uint64_t);
-        static bool attr = false;
+        static std::atomic<uint64_t> attr{0};
         const int rc = set_smem_attr_once(reinterpret_cast<const void*>(sp_tasks_kernel),
                                           kMaxOrderedSegs * (int)sizeof(uint64_t), &attr, "sd3d_sp_tasks");
         if (rc != SD3D_OK) return rc;

@@ -208,8 +208,10 @@ def scatter_mean(src: torch.Tensor, index: torch.Tensor, dim: int = -1, out: Opt
         s = 0
     else:
         s = int(index.max().item()) + 1
+    if index.dtype != torch.int64 or not index.is_contiguous():
+        index = index.to(torch.int64).contiguous()  # the kernels (forward AND backward) read int64 ids
     if src2.requires_grad and torch.is_grad_enabled():
-        res = _ScatterMeanFn.apply(src2, index, s, exact)
+        res = _ScatterMeanFn.apply(src2, index, s, exact, None)
         plan = None
     else:
         plan = _cached_plan(index, s)
@@ -233,9 +235,12 @@ class _ScatterMeanFn(torch.autograd.Function):
     """scatter_mean(src, index, dim=0) with the backward grad_src[p] = grad_out[index[p]] / max(|index[p]|, 1)."""
 
     @staticmethod
-    def forward(ctx, src2, index, n_segments, exact):
-        plan = sp_sort(index, n_segments)
-        ctx.save_for_backward(index.contiguous(), plan.seg_offsets)
+    def forward(ctx, src2, index, n_segments, exact, plan):
+        if index.dtype != torch.int64 or not index.is_contiguous():
+            index = index.to(torch.int64).contiguous()  # sd3d_sp_mean_backward reads `const int64_t* idx`
+        if plan is None:
+            plan = sp_sort(index, n_segments)
+        ctx.save_for_backward(index, plan.seg_offsets)
         ctx.n_segments = n_segments
         return sp_mean(src2, plan, exact=exact)
 
@@ -248,7 +253,15 @@ class _ScatterMeanFn(torch.autograd.Function):
         with torch.cuda.device(grad_out.device):
             check(_lib.load().sd3d_sp_mean_backward(_ptr(grad_out), _ptr(index), _ptr(seg_offsets), n, ctx.n_segments, c,
                                                     _ptr(grad_src), _stream()), "sd3d_sp_mean_backward")
-        return grad_src, None, None, None
+        return grad_src, None, None, None, None
+
+
+def sp_mean_autograd(src: torch.Tensor, index: torch.Tensor, plan: SuperpointPlan, exact: bool = True) -> torch.Tensor:
+    """``sp_mean`` that stays on the autograd tape (the pooling runs under autograd in training,
+    engine/train_engine_3d.py:99-105): several tensors pooled with ONE shared plan each keep their gradient."""
+    if src.requires_grad and torch.is_grad_enabled():
+        return _ScatterMeanFn.apply(src, index, plan.n_segments, exact, plan)
+    return sp_mean(src, plan, exact=exact)
 
 
 def expand_superpoint_masks(mask_pred_sigmoid: torch.Tensor, superpoints: torch.Tensor, sp_score_thr: float):
@@ -270,6 +283,27 @@ def expand_superpoint_masks(mask_pred_sigmoid: torch.Tensor, superpoints: torch.
         check(_lib.load().sd3d_sp_expand_mask(_ptr(m), _ptr(sp), k, s, n, float(sp_score_thr), _ptr(out), _ptr(pointnum),
                                               _stream()), "sd3d_sp_expand_mask")
     return out.view(torch.bool), pointnum.long()
+
+
+def superpoint_label_masks(labels: torch.Tensor, superpoints: torch.Tensor, num_classes: int,
+                           background_if_none: bool = False, n_superpoints: Optional[int] = None) -> torch.Tensor:
+    """``scatter_mean(F.one_hot(labels)[:, :num_classes].float(), superpoints, dim=0) > 0.5`` in one pass
+    (the superpoint-level ground truth of datasets/dataset/scannet200.py:243-253, scannet.py:204-211): bool
+    [S, num_classes]. Labels outside [0, num_classes) -- the reference maps -1 to the dropped last channel -- vote for
+    nobody. ``background_if_none``: rows without a winner get their last column set (scannet200.py:251)."""
+    _need_cuda("labels", labels)
+    _need_cuda("superpoints", superpoints)
+    labels = labels.reshape(-1).to(torch.int64).contiguous()
+    if superpoints.dim() != 1 or superpoints.numel() != labels.numel():
+        raise ValueError("labels and superpoints must have one entry per point")
+    plan = sp_sort(superpoints, n_superpoints)
+    k = int(num_classes)
+    with torch.cuda.device(labels.device):
+        out = torch.empty(plan.n_segments, k, dtype=torch.uint8, device=labels.device)
+        check(_lib.load().sd3d_sp_label_vote(_ptr(labels), _ptr(plan.perm), _ptr(plan.seg_offsets), labels.numel(),
+                                             plan.n_segments, k, 1 if background_if_none else 0, _ptr(out), _stream()),
+              "sd3d_sp_label_vote")
+    return out.view(torch.bool)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -372,14 +406,20 @@ def lift(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Ten
          stride: Optional[float] = None, *, tau: float = TAU_DEFAULT, z_near: float = Z_NEAR_DEFAULT,
          views: Optional[Tuple[int, int]] = None, finalize: bool = True, plan: Optional[SuperpointPlan] = None,
          pool: bool = False, want_maps: bool = False, accumulate_into: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
-         variant: int = 0, events: Optional[Tuple[torch.cuda.Event, torch.cuda.Event]] = None):
+         variant: int = 0, events: Optional[Tuple[torch.cuda.Event, torch.cuda.Event]] = None, k_views: int = 0):
     """One scale of the lifting path through ``sd3d_lift``.
 
     Returns a dict with ``feat`` [N,C] (mean over visible views if ``finalize`` else the raw sum),
     ``count`` [N] int32 and, on request, ``pix_idx`` / ``vis`` [V,N] and ``sp_feat`` [S,C] (``pool=True`` needs
     ``plan``; the plan's permutation is also used as the cache-friendly processing order).
     ``events`` (bench only): a pair of CUDA events recorded immediately before / after the gather kernel.
+    ``k_views`` > 0: nearest-view sampling (paper overview figure): only the k visible views with the smallest camera
+    depth are averaged (ties to the lower view index), ``count`` = min(visible views, k); ``pix_idx`` / ``vis`` still
+    report plain visibility.
     """
+    if not 0 <= int(k_views) <= 8:
+        raise ValueError("k_views must be in 0..8")
+    variant = int(variant) | (int(k_views) << 16)
     if pool and plan is None:
         raise ValueError("pool=True needs a SuperpointPlan (sp_sort)")
     if plan is not None and plan.n_points != xyz.shape[0]:

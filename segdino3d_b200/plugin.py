@@ -62,7 +62,8 @@ def pool_superpoints(tensors: Sequence[torch.Tensor], sp_pts_masks: torch.Tensor
     plan = ops.sp_sort(sp_pts_masks, batch_offsets[-1])
     out = []
     for t in tensors:
-        pooled = ops.sp_mean(t.float().contiguous(), plan, exact=exact)
+        # differentiable: x.features[inverse_mapping] requires grad in training (spconvunet.py:390)
+        pooled = ops.sp_mean_autograd(t.float().contiguous(), sp_pts_masks, plan, exact=exact)
         out.append([pooled[batch_offsets[i]: batch_offsets[i + 1]] for i in range(len(batch_offsets) - 1)])
     return out
 

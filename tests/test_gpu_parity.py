@@ -717,3 +717,67 @@ def test_push_exchange_emulated_on_one_device():
     got = torch.cat(feats)
     assert torch.isfinite(got).all()
     assert rel_row_err(got, ref["feat"][order], floor=1.0) <= 1e-5
+
+
+# ----------------------------------------------------------------------------------------------------
+# superpoint-level ground truth (second half)
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,s,k", [(20_000, 300, 37), (100_000, 521, 201), (5000, 40, 1500), (64, 70, 3)])
+def test_superpoint_label_masks_match_reference_text(n, s, k):
+    """scannet200.py:243-253 executed verbatim on CPU (one_hot -> scatter_mean -> > 0.5 [-> background]) against the
+    one-pass integer vote."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(n + k)
+    sp = torch.randint(0, s, (n,), generator=g)
+    # labels correlated with the superpoint (so that majorities exist), some background (-1), some exact ties
+    lab = (sp * 7 + torch.randint(0, 3, (n,), generator=g) // 2) % k
+    lab[torch.rand(n, generator=g) < 0.1] = -1
+    lab[:40] = torch.arange(40) % 2
+    sp[:40] = 0
+    inst = lab.clone()
+    inst[inst == -1] = int(inst.max() + 1)
+    onehot = F.one_hot(inst)[:, :-1]
+    want_inst = so.scatter_mean_oracle(onehot.float(), sp, dim=0) > 0.5
+    got = sd.superpoint_label_masks(lab.to(DEV), sp.to(DEV), onehot.shape[1])
+    assert got.dtype == torch.bool and torch.equal(got.cpu(), want_inst)
+    sem = lab.clone()
+    sem[sem == -1] = k  # the background class of the semantic one-hot
+    want_sem = so.scatter_mean_oracle(F.one_hot(sem, num_classes=k + 1).float(), sp, dim=0) > 0.5
+    want_sem[want_sem.sum(dim=-1) == 0, -1] = True
+    got_sem = sd.superpoint_label_masks(sem.to(DEV), sp.to(DEV), k + 1, background_if_none=True)
+    assert torch.equal(got_sem.cpu(), want_sem)
+
+
+@pytest.mark.parametrize("k", [1, 3, 8])
+def test_lift_nearest_view_sampling(k):
+    """SURVEY F8 variant: only the k nearest visible views (camera depth, ties to the lower view) are averaged."""
+    sc = make_scene(n_points=6000, n_views=24, hd=120, wd=160, stride=8, channels=64, seed=61, sp_target=50)
+    a, c, p, v = lo.lift_accumulate_oracle(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride, k_views=k)
+    assert int(c.max()) == k and int(v.sum(0).max()) > k  # the selection really bites
+    d = sc.to(DEV)
+    r = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, finalize=False, want_maps=True, k_views=k)
+    assert torch.equal(r["count"].cpu(), c) and torch.equal(r["vis"].cpu(), v) and torch.equal(r["pix_idx"].cpu(), p)
+    assert torch.equal(r["feat"].cpu(), a)
+    plan = sd.sp_sort(d.sp_ids, sc.n_superpoints, xyz=d.xyz)
+    r2 = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan, pool=True, k_views=k)
+    feat_o = lo.lift_finalize_oracle(a, c)
+    assert torch.equal(r2["feat"].cpu(), feat_o)
+    assert rel_row_err(r2["sp_feat"], so.scatter_mean_oracle(feat_o, sc.sp_ids, dim=0), floor=0.1) <= 1e-5
+
+
+def test_pool_superpoints_keeps_gradients_and_int32_ids():
+    """plugin.pool_superpoints must stay on the autograd tape (spconvunet.py:390 runs under autograd in
+    training), and an int32 index must not be reinterpreted as int64 by the backward kernel."""
+    g = torch.Generator().manual_seed(8)
+    n, s, c = 4000, 37, 32
+    ids = torch.randint(0, s, (n,), generator=g)
+    x_cpu = torch.randn(n, c, generator=g, requires_grad=True)
+    so.scatter_mean_oracle(x_cpu, ids, dim=0).square().sum().backward()
+    x = x_cpu.detach().to(DEV).requires_grad_(True)
+    pooled = plugin.pool_superpoints([x], ids.to(DEV), [0, s])[0][0]
+    assert pooled.requires_grad
+    pooled.square().sum().backward()
+    assert rel_row_err(x.grad, x_cpu.grad, floor=1e-3) <= 1e-5
+    x2 = x_cpu.detach().to(DEV).requires_grad_(True)
+    sd.scatter_mean(x2, ids.to(DEV).to(torch.int32), dim=0).square().sum().backward()
+    assert rel_row_err(x2.grad, x_cpu.grad, floor=1e-3) <= 1e-5

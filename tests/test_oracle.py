@@ -214,3 +214,23 @@ def test_mask_oracle_and_attn_epilogue():
     am = mo.attn_mask_oracle(pm, 0.5)
     assert am.dtype == torch.bool and not am[2].any()
     assert torch.equal(am[0], pm[0] < 0)
+
+
+def test_nearest_view_sampling_known_answer():
+    """k_views: a point seen by three cameras at depths 3, 1 and 2 metres keeps the two nearest (views 1, 2); a tie
+    keeps the lower view index."""
+    from oracle import lift_oracle as lo
+    xyz = torch.tensor([[0.0, 0.0, 0.0], [0.3, 0.0, 0.0]])
+    K = torch.tensor([[50.0, 50.0, 15.5, 11.5]]).repeat(4, 1)
+    w2c = torch.eye(4)[:3][None].repeat(4, 1, 1).contiguous()
+    for v, z in enumerate([3.0, 1.0, 2.0, 2.0]):
+        w2c[v, 2, 3] = z
+    depth = torch.stack([torch.full((24, 32), z) for z in (3.0, 1.0, 2.0, 2.0)])
+    fmap = torch.stack([torch.full((6, 8, 4), float(10 ** v)) for v in range(4)])
+    a, c, _, vis = lo.lift_accumulate_oracle(xyz, K, w2c, depth, fmap, 4.0, k_views=2)
+    assert vis.sum(0).tolist() == [4, 4] and c.tolist() == [2, 2]
+    assert torch.allclose(a[0], torch.full((4,), 10.0 + 100.0))          # views 1 (z=1) and 2 (z=2; tie with 3 -> lower index)
+    a3, c3, _, _ = lo.lift_accumulate_oracle(xyz, K, w2c, depth, fmap, 4.0, k_views=3)
+    assert c3.tolist() == [3, 3] and torch.allclose(a3[0], torch.full((4,), 1110.0))
+    a0, c0, _, _ = lo.lift_accumulate_oracle(xyz, K, w2c, depth, fmap, 4.0)
+    assert c0.tolist() == [4, 4] and torch.allclose(a0[0], torch.full((4,), 1111.0))
