@@ -203,6 +203,15 @@ int sd3d_scale_mean(const float* const* feats_host /*host array of L device ptrs
 int sd3d_mask_logits(const float* q, const float* mf, int n, int S, int d, int precision, float* out,
                      float thr, uint8_t* attn_mask, void* stream);
 
+/* The same contraction for every scene of a batch in ONE launch (the per-scene python loop of _forward_head,
+ * instance_seg_3d_decoder.py:557): problem i is q_host[i][n_host[i], d] x mf_host[i][S_host[i], d] -> out_host[i]
+ * (+ attn_host[i] when attn_host != NULL). The *_host arrays are HOST arrays of `count` device pointers / sizes.
+ * On the tensor-core path a CTA owns whole rows whenever S <= 512, and then the all-true-row reset of :570-571 is
+ * done in the same kernel (no second pass over the mask). */
+int sd3d_mask_logits_batched(const float* const* q_host, const float* const* mf_host, const int* n_host,
+                             const int* S_host, int count, int d, int precision, float* const* out_host, float thr,
+                             uint8_t* const* attn_host /*nullable*/, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * "next" rows of SURVEY 8(f)
  * --------------------------------------------------------------------------------------------- */

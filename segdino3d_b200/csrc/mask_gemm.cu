@@ -177,8 +177,9 @@ __device__ __forceinline__ void stage_operand(const float* __restrict__ g, int64
 
 // epilogue of one 128 x 64 accumulator stage: warp w reads TMEM lanes 32*(w&3)..+31 (= accumulator rows) and the
 // 32 columns of half (w>>2); thread = one row x 32 columns -> 128-bit stores
-__device__ __forceinline__ void tc_epilogue(uint32_t tmem_stage, int m0, int n0, int n, int S, float* __restrict__ out,
+__device__ __forceinline__ bool tc_epilogue(uint32_t tmem_stage, int m0, int n0, int n, int S, float* __restrict__ out,
                                             float thr, uint8_t* __restrict__ attn) {
+    bool all_true = true;  // of this thread's (row, 32-column) part, columns < S only
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const int c0 = (warp >> 2) * 32;
     const int gm = m0 + (warp & 3) * 32 + lane;
@@ -211,6 +212,7 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem_stage, int m0, int n0,
 #pragma unroll
                     for (int k = 0; k < 4; ++k) w |= (__uint_as_float(v[j + k]) < thr ? 1u : 0u) << (8 * k);
                     arow[j >> 2] = w;
+                    all_true &= w == 0x01010101u;
                 }
             }
         } else {
@@ -221,20 +223,26 @@ __device__ __forceinline__ void tc_epilogue(uint32_t tmem_stage, int m0, int n0,
                     const float val = __uint_as_float(v[j]);
                     out[(int64_t)gm * S + gn] = val;
                     if (attn) attn[(int64_t)gm * S + gn] = val < thr ? 1 : 0;  // thr is already a logit
+                    all_true &= val < thr;
                 }
             }
         }
     }
+    return all_true;
 }
 
 // One CTA = one 128-row block of queries x `tiles` consecutive 64-column tiles of superpoints. The A operand is
 // converted to bf16 once and stays in shared memory; B tiles and TMEM accumulators are STAGES-deep, so with
 // STAGES == 2 the tensor core works on tile t (async, tcgen05.commit -> mbarrier) while all warps write out
 // tile t-1 and then stage tile t+1: one __syncthreads per tile.
+// If the CTA owns ALL tiles of its rows (fuse_reset), the all-true-row reset of instance_seg_3d_decoder.py:570-571 is
+// done here: every thread tracks whether its part of its row was all-true, the two column halves meet in shared
+// memory, and the (rare) all-true rows are rewritten with zeros -- no second pass over the mask.
 template <int STAGES>
-__global__ void __launch_bounds__(kTcThreads)
-    mask_logits_tc_kernel(const float* __restrict__ q, const float* __restrict__ mf, int n, int S, int d, int tiles,
-                          float* __restrict__ out, float thr, uint8_t* __restrict__ attn) {
+__device__ __forceinline__ void mask_logits_tc_body(const float* __restrict__ q, const float* __restrict__ mf, int n,
+                                                    int S, int d, int tiles, float* __restrict__ out, float thr,
+                                                    uint8_t* __restrict__ attn, int m_block, int tile_group,
+                                                    bool fuse_reset) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment required by SWIZZLE_128B atoms
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -244,10 +252,12 @@ __global__ void __launch_bounds__(kTcThreads)
     uint8_t* sB = smem + a_bytes;
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ uint32_t s_tmem;
+    __shared__ uint8_t s_alltrue[2][kTcBM];
+    bool row_all_true = true;
 
     const int warp = threadIdx.x >> 5;
-    const int m0 = blockIdx.y * kTcBM;
-    const int nt0 = blockIdx.x * tiles;
+    const int m0 = m_block * kTcBM;
+    const int nt0 = tile_group * tiles;
     const int n_tiles_total = (S + kTcBN - 1) / kTcBN;
     const int my_tiles = min(tiles, n_tiles_total - nt0);
 
@@ -304,7 +314,7 @@ __global__ void __launch_bounds__(kTcThreads)
             if (t > 0) {
                 mbar_wait_parity(smem_u32(&s_bar[st ^ 1]), (uint32_t)(((t - 1) >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                tc_epilogue(tmem_base + (uint32_t)((st ^ 1) * kTcBN), m0, (nt0 + t - 1) * kTcBN, n, S, out, thr, attn);
+                row_all_true &= tc_epilogue(tmem_base + (uint32_t)((st ^ 1) * kTcBN), m0, (nt0 + t - 1) * kTcBN, n, S, out, thr, attn);
             }
             if (t + 1 < my_tiles) {  // stage st^1 is free: its MMAs (tile t-1) were waited for above
                 stage_operand<kTcBN>(mf, (int64_t)(nt0 + t + 1) * kTcBN, min(kTcBN, S - (nt0 + t + 1) * kTcBN), d,
@@ -314,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads)
         } else {
             mbar_wait_parity(smem_u32(&s_bar[0]), (uint32_t)(t & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            tc_epilogue(tmem_base, m0, (nt0 + t) * kTcBN, n, S, out, thr, attn);
+            row_all_true &= tc_epilogue(tmem_base, m0, (nt0 + t) * kTcBN, n, S, out, thr, attn);
             if (t + 1 < my_tiles) {
                 stage_operand<kTcBN>(mf, (int64_t)(nt0 + t + 1) * kTcBN, min(kTcBN, S - (nt0 + t + 1) * kTcBN), d, sB);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -328,9 +338,20 @@ __global__ void __launch_bounds__(kTcThreads)
         const int t = my_tiles - 1, st = t & 1;
         mbar_wait_parity(smem_u32(&s_bar[st]), (uint32_t)((t >> 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tc_epilogue(tmem_base + (uint32_t)(st * kTcBN), m0, (nt0 + t) * kTcBN, n, S, out, thr, attn);
+        row_all_true &= tc_epilogue(tmem_base + (uint32_t)(st * kTcBN), m0, (nt0 + t) * kTcBN, n, S, out, thr, attn);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
+    }
+    if (fuse_reset && attn != nullptr) {  // uniform over the CTA
+        s_alltrue[warp >> 2][(warp & 3) * 32 + lane_id()] = row_all_true ? 1 : 0;
+        __syncthreads();  // (also orders every warp's mask stores before the rewrite below)
+        if (warp < 4) {
+            const int r = warp * 32 + lane_id(), gm = m0 + r;
+            if (gm < n && s_alltrue[0][r] && s_alltrue[1][r]) {
+                uint8_t* arow = attn + (int64_t)gm * S;
+                for (int c = 0; c < S; ++c) arow[c] = 0;
+            }
+        }
     }
     if (warp == 0) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
@@ -339,9 +360,101 @@ __global__ void __launch_bounds__(kTcThreads)
     }
 }
 
+
+template <int STAGES>
+__global__ void __launch_bounds__(kTcThreads)
+    mask_logits_tc_kernel(const float* __restrict__ q, const float* __restrict__ mf, int n, int S, int d, int tiles,
+                          float* __restrict__ out, float thr, uint8_t* __restrict__ attn, int fuse_reset) {
+    mask_logits_tc_body<STAGES>(q, mf, n, S, d, tiles, out, thr, attn, blockIdx.y, blockIdx.x, fuse_reset != 0);
+}
+
+// ---- batched over the scenes of a batch (the per-scene python loop of _forward_head, instance_seg_3d_decoder.py:557):
+// one launch for all (scene, row block, tile group) CTAs
+constexpr int kMaxMaskProblems = 32;
+struct MaskProblem {
+    const float* q;
+    const float* mf;
+    float* out;
+    uint8_t* attn;
+    int n, S, cta_begin, tiles, groups, fuse_reset;
+};
+struct MaskBatch {
+    MaskProblem p[kMaxMaskProblems];
+    int count;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(kTcThreads)
+    mask_logits_tc_batched_kernel(const __grid_constant__ MaskBatch b, int d, float thr) {
+    int i = 0;
+    while (i + 1 < b.count && (int)blockIdx.x >= b.p[i + 1].cta_begin) ++i;
+    const MaskProblem& P = b.p[i];
+    const int local = (int)blockIdx.x - P.cta_begin;
+    mask_logits_tc_body<STAGES>(P.q, P.mf, P.n, P.S, d, P.tiles, P.out, thr, P.attn, local / P.groups, local % P.groups,
+                                P.fuse_reset != 0);
+}
+
+__global__ void attn_mask_fix_batched_kernel(const __grid_constant__ MaskBatch b) {
+    const MaskProblem& P = b.p[blockIdx.y];
+    if (P.attn == nullptr || P.fuse_reset) return;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= P.n) return;
+    const int lane = lane_id();
+    uint8_t* r = P.attn + (int64_t)row * P.S;
+    int all_true = 1;
+    for (int c = lane; c < P.S; c += 32) all_true &= (r[c] != 0);
+    all_true = __all_sync(kFull, all_true);
+    if (all_true)
+        for (int c = lane; c < P.S; c += 32) r[c] = 0;
+}
+
+// fp32 path, batched: one 32 x 32 tile per CTA, problems concatenated along blockIdx.x
+__global__ void __launch_bounds__(256) mask_logits_f32_batched_kernel(const __grid_constant__ MaskBatch b, int d, float thr) {
+    int i = 0;
+    while (i + 1 < b.count && (int)blockIdx.x >= b.p[i + 1].cta_begin) ++i;
+    const MaskProblem& P = b.p[i];
+    const int local = (int)blockIdx.x - P.cta_begin;
+    constexpr int BM = 32, BN = 32, BK = 32, TM = 2, TN = 2, NT = 256;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x, tx = tid % (BN / TN), ty = tid / (BN / TN);
+    const int m0 = (local / P.groups) * BM, n0 = (local % P.groups) * BN;
+    float acc[TM][TN] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int k0 = 0; k0 < d; k0 += BK) {
+        for (int e = tid; e < BM * BK; e += NT) {
+            const int r = e / BK, k = e % BK;
+            As[k][r] = (m0 + r < P.n && k0 + k < d) ? __ldg(P.q + (int64_t)(m0 + r) * d + k0 + k) : 0.f;
+        }
+        for (int e = tid; e < BN * BK; e += NT) {
+            const int r = e / BK, k = e % BK;
+            Bs[k][r] = (n0 + r < P.S && k0 + k < d) ? __ldg(P.mf + (int64_t)(n0 + r) * d + k0 + k) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+#pragma unroll
+            for (int a = 0; a < TM; ++a)
+#pragma unroll
+                for (int c = 0; c < TN; ++c) acc[a][c] = fmaf(As[k][ty * TM + a], Bs[k][tx * TN + c], acc[a][c]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int a = 0; a < TM; ++a)
+#pragma unroll
+        for (int c = 0; c < TN; ++c) {
+            const int gm = m0 + ty * TM + a, gn = n0 + tx * TN + c;
+            if (gm < P.n && gn < P.S) {
+                P.out[(int64_t)gm * P.S + gn] = acc[a][c];
+                if (P.attn) P.attn[(int64_t)gm * P.S + gn] = acc[a][c] < thr ? 1 : 0;
+            }
+        }
+}
 }  // namespace sd3d
 
 using namespace sd3d;
+
+static int set_tc_attributes();
 
 extern "C" int sd3d_mask_logits(const float* q, const float* mf, int n, int S, int d, int precision, float* out,
                                 float thr, uint8_t* attn_mask, void* stream_) {
@@ -360,6 +473,7 @@ extern "C" int sd3d_mask_logits(const float* q, const float* mf, int n, int S, i
         set_error("sd3d_mask_logits: null buffer");
         return SD3D_ERR_ARG;
     }
+    bool fused_reset = false;
     if (precision == SD3D_F32) {
         const bool big = ((int64_t)((n + 63) / 64) * ((S + 63) / 64)) >= 2 * (int64_t)num_sms();
         if (big) {
@@ -377,35 +491,121 @@ extern "C" int sd3d_mask_logits(const float* q, const float* mf, int n, int S, i
         }
         const int stages = d <= 256 ? 2 : 1;  // two B / TMEM stages fit beside a 128 x 256 bf16 A tile
         const size_t smem = (size_t)(d / kTcKBlock) * (kTcBM + stages * kTcBN) * 128 + 1024;
-        static std::atomic<uint64_t> attr_set{0};  // per-device flag (the attribute is per device)
-        if (first_on_device(&attr_set)) {
-            cudaError_t e = cudaFuncSetAttribute(mask_logits_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)(512 / kTcKBlock * (kTcBM + kTcBN) * 128 + 1024));
-            if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(mask_logits_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(256 / kTcKBlock * (kTcBM + 2 * kTcBN) * 128 + 1024));
-            if (e != cudaSuccess) {
-                attr_set.store(0);
-                set_error("sd3d_mask_logits: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-                return SD3D_ERR_CUDA;
-            }
-        }
+        const int rc_attr = set_tc_attributes();
+        if (rc_attr != SD3D_OK) return rc_attr;
         // N tiles per CTA: keep >= ~2 CTAs per SM in the grid, at most kTcMaxTiles per CTA
         const int n_tiles = (S + kTcBN - 1) / kTcBN, m_blocks = (n + kTcBM - 1) / kTcBM;
         int tiles = (int)(((int64_t)n_tiles * m_blocks) / (2 * (int64_t)num_sms()));
         if (tiles < 1) tiles = 1;
         if (tiles > kTcMaxTiles) tiles = kTcMaxTiles;
         dim3 grid((n_tiles + tiles - 1) / tiles, m_blocks);
+        fused_reset = attn_mask != nullptr && grid.x == 1;  // one CTA per row block sees whole rows
         if (stages == 2)
-            mask_logits_tc_kernel<2><<<grid, kTcThreads, smem, stream>>>(q, mf, n, S, d, tiles, out, thr, attn_mask);
+            mask_logits_tc_kernel<2><<<grid, kTcThreads, smem, stream>>>(q, mf, n, S, d, tiles, out, thr, attn_mask, fused_reset);
         else
-            mask_logits_tc_kernel<1><<<grid, kTcThreads, smem, stream>>>(q, mf, n, S, d, tiles, out, thr, attn_mask);
+            mask_logits_tc_kernel<1><<<grid, kTcThreads, smem, stream>>>(q, mf, n, S, d, tiles, out, thr, attn_mask, fused_reset);
     } else {
         set_error("sd3d_mask_logits: precision code %d unsupported (SD3D_F32 | SD3D_BF16)", precision);
         return SD3D_ERR_UNSUPPORTED;
     }
-    if (attn_mask != nullptr) {
+    if (attn_mask != nullptr && !fused_reset) {
         attn_mask_fix_kernel<<<(n + 7) / 8, 256, 0, stream>>>(attn_mask, n, S);
     }
     return check_launch("sd3d_mask_logits");
+}
+
+static int set_tc_attributes() {
+    static std::atomic<uint64_t> attr_set{0};  // per-device flag (the attribute is per device)
+    if (!first_on_device(&attr_set)) return SD3D_OK;
+    const int b1 = (int)(512 / kTcKBlock * (kTcBM + kTcBN) * 128 + 1024), b2 = (int)(256 / kTcKBlock * (kTcBM + 2 * kTcBN) * 128 + 1024);
+    cudaError_t e = cudaFuncSetAttribute(mask_logits_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mask_logits_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mask_logits_tc_batched_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, b1);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mask_logits_tc_batched_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, b2);
+    if (e != cudaSuccess) {
+        attr_set.store(0);
+        set_error("sd3d_mask_logits: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return SD3D_ERR_CUDA;
+    }
+    return SD3D_OK;
+}
+
+extern "C" int sd3d_mask_logits_batched(const float* const* q_host, const float* const* mf_host, const int* n_host,
+                                        const int* S_host, int count, int d, int precision, float* const* out_host,
+                                        float thr, uint8_t* const* attn_host, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (count < 0 || d <= 0 || (count > 0 && (q_host == nullptr || mf_host == nullptr || n_host == nullptr ||
+                                              S_host == nullptr || out_host == nullptr))) {
+        set_error("sd3d_mask_logits_batched: bad argument (count=%d d=%d)", count, d);
+        return SD3D_ERR_ARG;
+    }
+    if (precision != SD3D_F32 && precision != SD3D_BF16) {
+        set_error("sd3d_mask_logits_batched: precision code %d unsupported (SD3D_F32 | SD3D_BF16)", precision);
+        return SD3D_ERR_UNSUPPORTED;
+    }
+    const bool want_attn = attn_host != nullptr;
+    if (want_attn) {
+        const double t = (double)thr;
+        thr = t <= 0.0 ? -INFINITY : (t >= 1.0 ? INFINITY : (float)log(t / (1.0 - t)));
+    }
+    const int stages = d <= 256 ? 2 : 1;
+    if (precision == SD3D_BF16) {
+        if (d % kTcKBlock != 0 || d > 512) {
+            set_error("sd3d_mask_logits_batched: tcgen05 path needs d %% 64 == 0 and d <= 512 (d=%d)", d);
+            return SD3D_ERR_UNSUPPORTED;
+        }
+        const int rc = set_tc_attributes();
+        if (rc != SD3D_OK) return rc;
+    }
+    for (int base = 0; base < count; base += kMaxMaskProblems) {  // (a batch has a handful of scenes: one pass)
+        MaskBatch b;
+        b.count = 0;
+        int ctas = 0, max_n = 0;
+        bool any_unfused = false;
+        for (int i = base; i < count && b.count < kMaxMaskProblems; ++i) {
+            const int n = n_host[i], S = S_host[i];
+            if (n < 0 || S < 0) {
+                set_error("sd3d_mask_logits_batched: problem %d has a negative size", i);
+                return SD3D_ERR_ARG;
+            }
+            if (n == 0 || S == 0) continue;
+            if (q_host[i] == nullptr || mf_host[i] == nullptr || out_host[i] == nullptr ||
+                (precision == SD3D_BF16 && (!aligned16(q_host[i]) || !aligned16(mf_host[i])))) {
+                set_error("sd3d_mask_logits_batched: problem %d has a null or misaligned buffer", i);
+                return SD3D_ERR_ARG;
+            }
+            MaskProblem& P = b.p[b.count++];
+            P.q = q_host[i];
+            P.mf = mf_host[i];
+            P.out = out_host[i];
+            P.attn = want_attn ? attn_host[i] : nullptr;
+            P.n = n;
+            P.S = S;
+            P.cta_begin = ctas;
+            if (precision == SD3D_BF16) {
+                const int n_tiles = (S + kTcBN - 1) / kTcBN, m_blocks = (n + kTcBM - 1) / kTcBM;
+                P.tiles = n_tiles <= kTcMaxTiles ? n_tiles : kTcMaxTiles;  // whole rows per CTA when they fit
+                P.groups = (n_tiles + P.tiles - 1) / P.tiles;
+                P.fuse_reset = (P.attn != nullptr && P.groups == 1) ? 1 : 0;
+                ctas += m_blocks * P.groups;
+            } else {
+                P.tiles = 1;
+                P.groups = (S + 31) / 32;
+                P.fuse_reset = 0;
+                ctas += ((n + 31) / 32) * P.groups;
+            }
+            any_unfused |= P.attn != nullptr && !P.fuse_reset;
+            max_n = n > max_n ? n : max_n;
+        }
+        if (b.count == 0) continue;
+        if (precision == SD3D_BF16) {
+            const size_t smem = (size_t)(d / kTcKBlock) * (kTcBM + stages * kTcBN) * 128 + 1024;
+            if (stages == 2) mask_logits_tc_batched_kernel<2><<<ctas, kTcThreads, smem, stream>>>(b, d, thr);
+            else mask_logits_tc_batched_kernel<1><<<ctas, kTcThreads, smem, stream>>>(b, d, thr);
+        } else {
+            mask_logits_f32_batched_kernel<<<ctas, 256, 0, stream>>>(b, d, thr);
+        }
+        if (any_unfused) attn_mask_fix_batched_kernel<<<dim3((max_n + 7) / 8, b.count), 256, 0, stream>>>(b);
+    }
+    return check_launch("sd3d_mask_logits_batched");
 }

@@ -201,7 +201,9 @@ def lift_view_sharded_p2p(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: t
 
     Returns ``feat_shard`` [rows,C] for processing positions ``rows=(begin,end)`` (point ids ``pids``),
     ``count_shard`` [rows] and ``sp_feat`` [S,C] (identical on all ranks). ``step`` selects the staging buffer
-    (consecutive scenes must alternate). ``cache``: a dict the caller keeps between scenes of the same shape; the
+    (consecutive scenes must alternate; two consecutive scenes may be in flight on two CUDA streams: everything a
+    scene touches is indexed by ``step % 2``, and scene k+2 is ordered after scene k's owner-side reduce on every
+    rank by scene k's final all_reduce). ``cache``: a dict the caller keeps between scenes of the same shape; the
     workspace and the output buffers then live in it instead of being allocated per scene (results of a scene are
     overwritten by the scene after next)."""
     from . import ops
@@ -225,13 +227,13 @@ def lift_view_sharded_p2p(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: t
     bufs = cache.get("bufs") if cache is not None else None
     if bufs is None or bufs["key"] != key:
         extra = (s + c - 1) // c  # the superpoint sizes ride in `extra` trailing rows of the [S,C] all_reduce buffer
-        bufs = {"key": key, "ws": None, "token": torch.zeros(1, device=dev),
+        bufs = {"key": key, "ws": None, "token": [torch.zeros(1, device=dev) for _ in range(2)],
                 "feat": [torch.empty(rows, c, dtype=torch.float32, device=dev) for _ in range(2)],
                 "cnt": [torch.empty(rows, dtype=torch.int32, device=dev) for _ in range(2)],
                 "sp": [torch.empty(s + extra, c, dtype=torch.float32, device=dev) for _ in range(2)],
                 "ident": torch.arange(rows, dtype=torch.int32, device=dev)}
         ws_bytes = int(ops._lib.load().sd3d_lift_workspace_bytes(n, K_local.shape[0], c, 0))
-        bufs["ws"] = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        bufs["ws"] = [torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev) for _ in range(2)]
         if cache is not None:
             cache["bufs"] = bufs
     mark("start")
@@ -241,9 +243,9 @@ def lift_view_sharded_p2p(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: t
     mark("plan")
     ops.lift_push(xyz, K_local, w2c_local, depth_local, fmap_local, stride, plan, n_ranks=world, src_rank=rank,
                   rows_per_rank=stage.rows, peer_sum=stage.sum_ptrs[b], peer_count=stage.cnt_ptrs[b], tau=tau,
-                  z_near=z_near, variant=variant, ws=bufs["ws"])
+                  z_near=z_near, variant=variant, ws=bufs["ws"][b])
     mark("project+gather+push")
-    dist.all_reduce(bufs["token"], group=group)  # barrier on the stream: every rank's gather (and its peer stores) is complete
+    dist.all_reduce(bufs["token"][b], group=group)  # barrier on the stream: every rank's gather (and its peer stores) is complete
     mark("barrier")
     feat_shard, cnt_shard = ops.push_reduce(stage.sum_ptrs[b][rank], stage.cnt_ptrs[b][rank], world, stage.rows, rows, c,
                                             dev, out=(bufs["feat"][b], bufs["cnt"][b]))
@@ -267,7 +269,7 @@ def lift_view_sharded_p2p(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: t
 
 
 def measure_viewshard(wl: dict, exchange: str, steps: int, warmup: int, rank: int, world: int, dev: torch.device,
-                      variant: int = 0, stage_times: bool = False):
+                      variant: int = 0, stage_times: bool = False, pipelined: bool = True):
     """Times `steps` view-sharded lifts of one scene of workload `wl` on `world` ranks (world == 1: the whole scene
     on this rank, no exchange). Every rank builds the same scene and keeps its contiguous view range. Device time
     with CUDA events, max over ranks. Returns (ms_per_step, n_superpoints, clocks)."""
@@ -299,8 +301,21 @@ def measure_viewshard(wl: dict, exchange: str, steps: int, warmup: int, rank: in
         return lift_view_sharded(d["xyz"], K_l, w2c_l, depth_l, fmap_l, d["sp_ids"], sc.n_superpoints,
                                  stride=sc.stride, exchange=ex, ops=ops, world=world)
 
-    for _ in range(max(warmup, 3)):
-        step()
+    # two scenes in flight on two streams (throughput mode, like the replicas' --streams 2): the latency-bound plan and
+    # the owner-side tail of one scene overlap with the gather of the next
+    main = torch.cuda.current_stream()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()] if (stage is not None and pipelined) else [main]
+
+    def run(k):
+        for st in streams:
+            st.wait_stream(main)
+        for i in range(k):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                step()
+        for st in streams:
+            main.wait_stream(st)
+
+    run(max(warmup, 3) + (max(warmup, 3) % 2))  # (an even count keeps step parity == stream parity)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -309,14 +324,15 @@ def measure_viewshard(wl: dict, exchange: str, steps: int, warmup: int, rank: in
     torch.cuda.synchronize()
     sampler.start()
     e0.record()
-    for _ in range(steps):
-        step()
+    run(steps)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     clocks = sampler.stop()
     ms = e0.elapsed_time(e1) / steps
+    if steps % 2:
+        step()  # keep step parity == stream parity for whoever runs next
     if stage is not None and stage_times:
         acc = {}
         for _ in range(10):
@@ -361,7 +377,7 @@ def viewshard_report(wl: dict, workload: str, exchange: str, steps: int, warmup:
                     "speedup_vs_1gpu": ms_1 / ms_n, "scaling": "strong",
                     "note": "views of ONE scene sharded over the ranks; p2p = partial rows stored by the gather kernel "
                             "straight into the owner rank's staging buffer over NVLink (sd3d_lift_push), one barrier, "
-                            "owner-side reduce + pooling, one all_reduce of [S,C+1]"})
+                            "owner-side reduce + pooling, one all_reduce of [S,C+1]; two scenes in flight on two CUDA streams"})
     return out
 
 

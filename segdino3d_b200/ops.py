@@ -673,6 +673,49 @@ class _MaskLogitsFn(torch.autograd.Function):
         return grad_q, grad_mf, None, None
 
 
+def mask_logits_batched(queries: Sequence[torch.Tensor], mask_feats: Sequence[torch.Tensor], precision: str = "fp32",
+                        threshold: Optional[float] = None):
+    """``mask_logits`` for every scene of a batch in ONE launch (``_forward_head`` loops over the batch in python,
+    instance_seg_3d_decoder.py:557). Returns (list of pred_masks, list of attn_masks or None). Forward only (no
+    autograd: under grad mode it falls back to one differentiable call per scene)."""
+    if len(queries) != len(mask_feats):
+        raise ValueError("need one mask-feature tensor per query tensor")
+    code = {"fp32": _lib.F32, "f32": _lib.F32, "bf16": _lib.BF16}.get(precision)
+    if code is None:
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if len(queries) == 0:
+        return [], ([] if threshold is not None else None)
+    if torch.is_grad_enabled() and any(t.requires_grad for t in list(queries) + list(mask_feats)):
+        res = [mask_logits(q, mf, precision=precision, threshold=threshold) for q, mf in zip(queries, mask_feats)]
+        if threshold is None:
+            return res, None
+        return [r[0] for r in res], [r[1] for r in res]
+    d = queries[0].shape[1]
+    qs, mfs = [], []
+    for q, mf in zip(queries, mask_feats):
+        _need_cuda("queries[i]", q)
+        _need_cuda("mask_feats[i]", mf)
+        if q.dim() != 2 or mf.dim() != 2 or q.shape[1] != d or mf.shape[1] != d:
+            raise ValueError("every scene needs [n_i, d] queries and [S_i, d] mask features with one d")
+        if q.dtype != torch.float32 or mf.dtype != torch.float32:
+            raise Sd3dError("mask_logits takes float32 operands (the reference runs amp=False)")
+        qs.append(q.contiguous())
+        mfs.append(mf.contiguous())
+    dev = qs[0].device
+    k = len(qs)
+    with torch.cuda.device(dev):
+        outs = [torch.empty(q.shape[0], mf.shape[0], dtype=torch.float32, device=dev) for q, mf in zip(qs, mfs)]
+        attns = [torch.empty(o.shape, dtype=torch.uint8, device=dev) for o in outs] if threshold is not None else None
+        ptr_arr = ctypes.c_void_p * k
+        int_arr = ctypes.c_int * k
+        check(_lib.load().sd3d_mask_logits_batched(
+            ptr_arr(*[t.data_ptr() for t in qs]), ptr_arr(*[t.data_ptr() for t in mfs]),
+            int_arr(*[t.shape[0] for t in qs]), int_arr(*[t.shape[0] for t in mfs]), k, d, code,
+            ptr_arr(*[t.data_ptr() for t in outs]), float(threshold) if threshold is not None else 0.0,
+            ptr_arr(*[t.data_ptr() for t in attns]) if attns is not None else None, _stream()), "sd3d_mask_logits_batched")
+    return outs, ([a.view(torch.bool) for a in attns] if attns is not None else None)
+
+
 def mask_logits(q: torch.Tensor, mf: torch.Tensor, precision: str = "fp32", threshold: Optional[float] = None):
     """``torch.einsum('nd,md->nm', q, mf)`` (instance_seg_3d_decoder.py:567). ``precision='bf16'`` runs the
     tcgen05 tensor-core kernel (bf16 operands, fp32 accumulate). With ``threshold`` also returns the fused

@@ -72,6 +72,11 @@ def forward_head_masks(norm_queries: Sequence[torch.Tensor], mask_feats: Sequenc
                        mask_attention_threshold: Optional[float], precision: str = "fp32"):
     """instance_seg_3d_decoder.py:567-574 for a batch given as python lists (one entry per scene):
     returns (pred_masks, attn_masks or None)."""
+    if not (torch.is_grad_enabled() and any(t.requires_grad for t in list(norm_queries) + list(mask_feats))):
+        # inference: every scene of the batch in one launch, row reset fused into the GEMM epilogue
+        pred, attn = ops.mask_logits_batched(norm_queries, mask_feats, precision=precision,
+                                             threshold=mask_attention_threshold)
+        return pred, ([a.detach() for a in attn] if attn is not None else None)
     pred_masks, attn_masks = [], []
     for q, mf in zip(norm_queries, mask_feats):
         if mask_attention_threshold is not None:

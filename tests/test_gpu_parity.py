@@ -781,3 +781,34 @@ def test_pool_superpoints_keeps_gradients_and_int32_ids():
     x2 = x_cpu.detach().to(DEV).requires_grad_(True)
     sd.scatter_mean(x2, ids.to(DEV).to(torch.int32), dim=0).square().sum().backward()
     assert rel_row_err(x2.grad, x_cpu.grad, floor=1e-3) <= 1e-5
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
+def test_mask_logits_batched_one_launch(precision, tol):
+    """Every scene of a batch in one launch (instance_seg_3d_decoder.py:557 loops in python); whole rows per CTA ->
+    the all-true-row reset (:570-571) happens inside the GEMM kernel. Shapes include S > 512 (split rows: separate
+    reset pass), S not a multiple of 4, a single-query scene and an empty scene."""
+    g = torch.Generator().manual_seed(12)
+    shapes = [(200, 500), (37, 97), (1, 64), (150, 1303), (0, 50), (129, 511)]
+    qs = [torch.nn.functional.layer_norm(torch.randn(n, 256, generator=g), (256,)) for n, _ in shapes]
+    mfs = [0.3 * torch.randn(s, 256, generator=g) for _, s in shapes]
+    mfs[1] = mfs[1] - 0.05 * qs[1][5][None, :]  # scene 1, query 5: every logit negative -> all-true row before the reset
+    pred, attn = sd.mask_logits_batched([q.to(DEV) for q in qs], [m.to(DEV) for m in mfs], precision=precision, threshold=0.5)
+    for i, (q, mf) in enumerate(zip(qs, mfs)):
+        want = mo.mask_logits_oracle(q, mf)
+        assert pred[i].shape == want.shape and attn[i].shape == want.shape and attn[i].dtype == torch.bool
+        if want.numel() == 0:
+            continue
+        scale = want.abs().amax(dim=1, keepdim=True).clamp(min=1.0)
+        assert float(((pred[i].cpu() - want).abs() / scale).max()) <= tol
+        # the mask is judged on the kernel's own logits (what the epilogue thresholds), away from the threshold
+        mine = pred[i].cpu()
+        want_attn = mo.attn_mask_oracle(mine, 0.5)
+        decided = mine.abs() > 1e-6
+        rows_ok = (want_attn.sum(-1) == mo.attn_mask_oracle(torch.where(decided, mine, torch.ones_like(mine)), 0.5).sum(-1))
+        assert torch.equal(attn[i].cpu()[rows_ok], want_attn[rows_ok])
+    assert not attn[1][5].any()
+    one = sd.mask_logits(qs[0].to(DEV), mfs[0].to(DEV), precision=precision, threshold=0.5)
+    assert torch.equal(one[0], pred[0]) and torch.equal(one[1], attn[0])
+    nothr, none = sd.mask_logits_batched([qs[0].to(DEV)], [mfs[0].to(DEV)], precision=precision)
+    assert none is None and torch.equal(nothr[0], pred[0])
