@@ -32,6 +32,10 @@ if ROOT not in sys.path:
 WORKLOADS = {
     # BASELINE.json configs[1] (== configs[0] shape): the configuration the metric is quoted on
     "cfg2": dict(n_points=100_000, n_views=40, hd=480, wd=640, stride=8, channels=256, sp_voxel=0.6, sp_target=500),
+    # configs[2]: the same scene shape with fp16 DINO-X maps and ScanNet-native u16 depth (the 8-scene batch is the
+    # replica mode at --gpus 8); the SpConvUNet pooling width of that prototype (C=32) is timed by tools/bench_ops.py
+    "cfg3": dict(n_points=100_000, n_views=40, hd=480, wd=640, stride=8, channels=256, sp_voxel=0.6, sp_target=500,
+                 fmap_dtype="float16", depth_u16=True),
     # configs[3]: large scene
     "cfg4": dict(n_points=1_000_000, n_views=300, hd=480, wd=640, stride=8, channels=256, sp_voxel=0.2,
                  sp_target=5000),
@@ -41,6 +45,23 @@ WORKLOADS = {
     # tiny, for CPU-side plumbing checks of this script
     "tiny": dict(n_points=4000, n_views=6, hd=120, wd=160, stride=8, channels=64, sp_voxel=0.6, sp_target=40),
 }
+
+
+def build_scene(wl: dict, seed: int, fmap_device=None):
+    """make_scene for a WORKLOADS entry (handles the dtype keys)."""
+    import torch
+    from segdino3d_b200.synth import make_scene
+    kw = {k: v for k, v in wl.items() if k not in ("fmap_dtype", "depth_u16")}
+    if "fmap_dtype" in wl:
+        kw["fmap_dtype"] = getattr(torch, wl["fmap_dtype"])
+    sc = make_scene(seed=seed, fmap_device=fmap_device, **kw)
+    if wl.get("depth_u16"):
+        sc.depth = sc.depth_u16()
+    return sc
+
+
+def elem_sizes(wl: dict):
+    return (2 if wl.get("fmap_dtype") in ("float16", "bfloat16") else 4), (2 if wl.get("depth_u16") else 4)
 
 
 def algorithmic_bytes(n, v, hd, wd, hf, wf, c, s, sf=4, sd_=4):
@@ -168,7 +189,7 @@ def run_reference(args):
     cores = c_ref.use_all_host_threads()  # torchrun exports OMP_NUM_THREADS=1: the arm must still use every host core
     assert cores > 1 or (os.cpu_count() or 1) == 1, f"reference arm runs on {cores} thread(s) of {os.cpu_count()} CPUs"
     wl = WORKLOADS[args.workload]
-    sc = make_scene(seed=1235, **wl)
+    sc = build_scene(wl, 1235)
     cpu_reference_step(sc)
     t0 = time.perf_counter()
     cpu_reference_step(sc)
@@ -236,15 +257,17 @@ def run_ours(args):
     n_rot = args.rotate
     scenes = []
     for i in range(n_rot):
-        sc = make_scene(seed=1235 + i + 1000 * rank, fmap_device=dev, **wl)
+        sc = build_scene(wl, 1235 + i + 1000 * rank, fmap_device=dev)
         scenes.append(sc.to(dev))
     n, v = wl["n_points"], wl["n_views"]
     hf, wf, c = wl["hd"] // wl["stride"], wl["wd"] // wl["stride"], wl["channels"]
     s_max = max(sc.n_superpoints for sc in scenes)
-    b_lift, b_path = algorithmic_bytes(n, v, wl["hd"], wl["wd"], hf, wf, c, scenes[0].n_superpoints)
+    sf, sdep = elem_sizes(wl)
+    scene_mb = int((v * (hf * wf * c * sf + wl["hd"] * wl["wd"] * sdep) + n * 20) / 1e6)
+    b_lift, b_path = algorithmic_bytes(n, v, wl["hd"], wl["wd"], hf, wf, c, scenes[0].n_superpoints, sf, sdep)
     # the dominant kernel (gather) alone: maps once, per-point view masks, xyz, cameras in; features + count out
     # (the visible-pair term is filled in after the warm-up, when the count of visible (point, view) pairs is known)
-    b_gather_fixed = v * hf * wf * c * 4 + n * 4 + n * 4 + n * c * 4 + n * 4  # maps, order, nvis in; features, count out
+    b_gather_fixed = v * hf * wf * c * sf + n * 4 + n * 4 + n * c * 4 + n * 4  # maps, order, nvis in; features, count out
 
     bufs = {}  # (scene, stream slot) -> persistent outputs + workspace: the timed step allocates nothing
 
@@ -297,7 +320,7 @@ def run_ours(args):
             step(scenes[i % n_rot], slot=i % len(streams))
     torch.cuda.synchronize()
     b_gather = int(b_gather_fixed)  # compulsory bytes only: the K1 -> K2 sample records are an implementation intermediate
-    l1_bytes = pairs * 4 * c * 4
+    l1_bytes = pairs * 4 * c * sf
     run_steps(max(args.warmup, 3))
     torch.cuda.synchronize()
     if args.graph:
@@ -408,9 +431,10 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "n_points": n, "n_views": v, "depth": [wl["hd"], wl["wd"]],
+                       "fmap_dtype": wl.get("fmap_dtype", "float32"), "depth_dtype": "uint16 mm" if wl.get("depth_u16") else "float32 m",
                        "fmap": [hf, wf, c], "stride": wl["stride"], "n_superpoints": n_sp0,
                        "parallelism": "scene replicas (no collective)" if world > 1 else "single GPU",
-                       "l2": f"inputs rotate over {n_rot} distinct scenes ({n_rot * 248} MB > 126 MB L2), no flush",
+                       "l2": f"inputs rotate over {n_rot} distinct scenes ({n_rot * scene_mb} MB > 126 MB L2), no flush",
                        "run": args.run, "variant": args.variant, "streams": len(streams),
                        "projection_overlaps_plan": not args.no_overlap, "cuda_graph": bool(args.graph)},
             "points_per_s": value * n, "host_us_per_step": host_us,
@@ -435,7 +459,7 @@ def run_ours(args):
         if viewshard is not None:
             line["viewshard"] = viewshard
         if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(make_scene(seed=1235, **wl))
+            line["cpu_baseline"] = cpu_baseline(build_scene(wl, 1235))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -189,9 +189,9 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const __grid
     float4 sp_acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) sp_acc[k] = f4_zero();
-    Sample<NV> sa, sb;  // lanes beyond C never load: give their registers a defined value once
-    sample_clear<NV>(sa);
-    sample_clear<NV>(sb);
+    Sample<NV, FT> sa, sb;  // lanes beyond C never load: give their registers a defined value once
+    sample_clear<NV, FT>(sa);
+    sample_clear<NV, FT>(sb);
 
     for (int64_t i = start + warp; i < end; i += kLiftWarps) {
         const int32_t pid = p.order ? p.order[i] : (int32_t)i;
@@ -222,16 +222,16 @@ __global__ void __launch_bounds__(kLiftThreads, MINB) gather_kernel(const __grid
                 int sidx = 0;
                 while (true) {
                     if (sidx + 1 < n_round) sample_issue<NV, FT>(sb, mine, sidx + 1, p.C, row_elems, lane, cmask);
-                    sample_accum<NV, FAST>(acc, sa);
+                    sample_accum<NV, FAST, FT>(acc, sa);
                     if (++sidx >= n_round) break;
                     if (sidx + 1 < n_round) sample_issue<NV, FT>(sa, mine, sidx + 1, p.C, row_elems, lane, cmask);
-                    sample_accum<NV, FAST>(acc, sb);
+                    sample_accum<NV, FAST, FT>(acc, sb);
                     if (++sidx >= n_round) break;
                 }
             } else {  // wide rows (C > 512): one sample in flight, the tap rows alone fill the register file
                 for (int sidx = 0; sidx < n_round; ++sidx) {
                     sample_issue<NV, FT>(sa, mine, sidx, p.C, row_elems, lane, cmask);
-                    sample_accum<NV, FAST>(acc, sa);
+                    sample_accum<NV, FAST, FT>(acc, sa);
                 }
             }
         }
@@ -321,9 +321,9 @@ __global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePt
     float4 sp_acc[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) sp_acc[k] = f4_zero();
-    Sample<NV> sa, sb;
-    sample_clear<NV>(sa);
-    if (DB) sample_clear<NV>(sb);
+    Sample<NV, FT> sa, sb;
+    sample_clear<NV, FT>(sa);
+    if (DB) sample_clear<NV, FT>(sb);
 
     for (int64_t t0 = start; t0 < end; t0 += kTilePts) {  // one pass when run == 32
         // lanes 0..3 of every warp own one point each
@@ -431,18 +431,18 @@ __global__ void __launch_bounds__(32 * (kTilePts / kTileG), 512 / (32 * (kTilePt
                 // static schedule, two samples in flight: A<-0, B<-1, use A, A<-2, use B, B<-3, use A, use B
                 if (vm_cur & 1u) sample_issue<NV, FT>(sa, cur, 0, p.C, row_elems, lane, cmask);
                 if (vm_cur & 2u) sample_issue<NV, FT>(sb, cur, 1, p.C, row_elems, lane, cmask);
-                if (vm_cur & 1u) sample_accum<NV, FAST>(acc[0], sa);
+                if (vm_cur & 1u) sample_accum<NV, FAST, FT>(acc[0], sa);
                 if (vm_cur & 4u) sample_issue<NV, FT>(sa, cur, 2, p.C, row_elems, lane, cmask);
-                if (vm_cur & 2u) sample_accum<NV, FAST>(acc[1], sb);
+                if (vm_cur & 2u) sample_accum<NV, FAST, FT>(acc[1], sb);
                 if (vm_cur & 8u) sample_issue<NV, FT>(sb, cur, 3, p.C, row_elems, lane, cmask);
-                if (vm_cur & 4u) sample_accum<NV, FAST>(acc[2], sa);
-                if (vm_cur & 8u) sample_accum<NV, FAST>(acc[3], sb);
+                if (vm_cur & 4u) sample_accum<NV, FAST, FT>(acc[2], sa);
+                if (vm_cur & 8u) sample_accum<NV, FAST, FT>(acc[3], sb);
             } else {  // rows were prefetched into L1 one view ahead: a single register buffer suffices
 #pragma unroll
                 for (int j = 0; j < kTileG; ++j) {
                     if (vm_cur & (1u << j)) {
                         sample_issue<NV, FT>(sa, cur, j, p.C, row_elems, lane, cmask);
-                        sample_accum<NV, FAST>(acc[j], sa);
+                        sample_accum<NV, FAST, FT>(acc[j], sa);
                     }
                 }
             }
@@ -777,12 +777,7 @@ static int lift_impl(const float* xyz, int64_t N, const float* K4, const float* 
     int rc;
     if (!do_gather) return check_launch("sd3d_lift(project)");
     switch (fmap_dtype) {
-        case SD3D_F32:
-            if ((variant & 16384) && C % 8 == 0 && (reinterpret_cast<uintptr_t>(fmap) & 31u) == 0)  // experiment: LDG.256
-                rc = dispatch_gather<F32x8>(p, masks, nchunks, n_tasks, variant, stream);
-            else
-                rc = dispatch_gather<float>(p, masks, nchunks, n_tasks, variant, stream);
-            break;
+        case SD3D_F32: rc = dispatch_gather<float>(p, masks, nchunks, n_tasks, variant, stream); break;
         case SD3D_F16: rc = dispatch_gather<__half>(p, masks, nchunks, n_tasks, variant, stream); break;
         case SD3D_BF16: rc = dispatch_gather<__nv_bfloat16>(p, masks, nchunks, n_tasks, variant, stream); break;
         default:

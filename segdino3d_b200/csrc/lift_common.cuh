@@ -56,38 +56,29 @@ struct LiftParams {
     int n_views;
 };
 
-// One 128-bit load per lane per tap row: 4 fp32 channels, or 8 fp16 / bf16 channels (= two float4 registers).
+// One 128-bit load per lane per tap row: 4 fp32 channels, or 8 fp16 / bf16 channels (= two float4 registers once
+// decoded). The loaded word stays RAW while the load is in flight (`Raw`); it is decoded to fp32 when the sample is
+// blended, so that the conversion instructions never wait on a load that was only just issued.
 // chan_of(k, lane) = first channel held by float4 register k of this lane.
 template <typename FT>
 struct Tap;
 template <>
 struct Tap<float> {
     static constexpr int kElems = 4, kRegs = 1;
-    __device__ __forceinline__ static void load(float4* dst, const float* p) {
-        dst[0] = __ldg(reinterpret_cast<const float4*>(p));
-    }
-};
-// fp32 rows read with ONE 256-bit load per lane and tap (sm_100 LDG.256): 8 consecutive channels = two float4 registers
-struct F32x8 {
-    float v;
-};
-template <>
-struct Tap<F32x8> {
-    static constexpr int kElems = 8, kRegs = 2;
-    __device__ __forceinline__ static void load(float4* dst, const F32x8* p) {
-        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                     : "=f"(dst[0].x), "=f"(dst[0].y), "=f"(dst[0].z), "=f"(dst[0].w), "=f"(dst[1].x), "=f"(dst[1].y),
-                       "=f"(dst[1].z), "=f"(dst[1].w)
-                     : "l"(p));
-    }
+    typedef float4 Raw;
+    __device__ __forceinline__ static Raw zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ static Raw load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+    __device__ __forceinline__ static Raw from_smem(const uint8_t* p) { return *reinterpret_cast<const float4*>(p); }
+    __device__ __forceinline__ static void decode(float4* dst, const Raw raw) { dst[0] = raw; }
 };
 template <>
 struct Tap<__half> {
     static constexpr int kElems = 8, kRegs = 2;
-    __device__ __forceinline__ static void load(float4* dst, const __half* p) {
-        decode(dst, __ldg(reinterpret_cast<const uint4*>(p)));
-    }
-    __device__ __forceinline__ static void decode(float4* dst, const uint4 raw) {
+    typedef uint4 Raw;
+    __device__ __forceinline__ static Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+    __device__ __forceinline__ static Raw load(const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ static Raw from_smem(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ static void decode(float4* dst, const Raw raw) {
         const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
         const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
         const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&raw.z));
@@ -99,10 +90,11 @@ struct Tap<__half> {
 template <>
 struct Tap<__nv_bfloat16> {
     static constexpr int kElems = 8, kRegs = 2;
-    __device__ __forceinline__ static void load(float4* dst, const __nv_bfloat16* p) {
-        decode(dst, __ldg(reinterpret_cast<const uint4*>(p)));
-    }
-    __device__ __forceinline__ static void decode(float4* dst, const uint4 raw) {
+    typedef uint4 Raw;
+    __device__ __forceinline__ static Raw zero() { return make_uint4(0u, 0u, 0u, 0u); }
+    __device__ __forceinline__ static Raw load(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+    __device__ __forceinline__ static Raw from_smem(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+    __device__ __forceinline__ static void decode(float4* dst, const Raw raw) {
         dst[0] = make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
                              __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
         dst[1] = make_float4(__uint_as_float(raw.z << 16), __uint_as_float(raw.z & 0xffff0000u),
@@ -176,11 +168,12 @@ __device__ __forceinline__ void blend2(float& ax, float& ay, const Weights2& w, 
     unpk2(r, ax, ay);
 }
 
-// One bilinear sample in flight: the four tap rows (this lane's channel vectors) + the weights.
-template <int NV>
+// One bilinear sample in flight: the four tap rows (this lane's channel vectors, still raw) + the weights.
+// NV = float4 accumulator registers per lane; a raw tap word decodes to Tap<FT>::kRegs of them.
+template <int NV, typename FT>
 struct Sample {
     float w00, w01, w10, w11;
-    float4 t00[NV], t01[NV], t10[NV], t11[NV];
+    typename Tap<FT>::Raw t00[NV / Tap<FT>::kRegs], t01[NV / Tap<FT>::kRegs], t10[NV / Tap<FT>::kRegs], t11[NV / Tap<FT>::kRegs];
 };
 
 // Per-sample scalars, computed ONCE by the lane that owns the sample (Appendix A lines `uf = ...` ..
@@ -281,10 +274,10 @@ __device__ __forceinline__ SampleScalars scalars_from_record(const int4 rec, con
 }
 
 template <int NV, typename FT>
-__device__ __forceinline__ void sample_issue_loads(Sample<NV>& s, uint32_t lo, uint32_t hi, int C, int row_elems, int lane,
+__device__ __forceinline__ void sample_issue_loads(Sample<NV, FT>& s, uint32_t lo, uint32_t hi, int C, int row_elems, int lane,
                                                    unsigned cmask);
 template <int NV, typename FT>
-__device__ __forceinline__ void sample_issue(Sample<NV>& s, const SampleScalars& mine, int src_lane, int C,
+__device__ __forceinline__ void sample_issue(Sample<NV, FT>& s, const SampleScalars& mine, int src_lane, int C,
                                              int row_elems, int lane, unsigned cmask) {
     const uint32_t lo = __shfl_sync(kFull, mine.addr_lo, src_lane);
     const uint32_t hi = __shfl_sync(kFull, mine.addr_hi, src_lane);
@@ -296,7 +289,7 @@ __device__ __forceinline__ void sample_issue(Sample<NV>& s, const SampleScalars&
 }
 // the loads of one sample given its (warp-uniform) packed tap address + flags
 template <int NV, typename FT>
-__device__ __forceinline__ void sample_issue_loads(Sample<NV>& s, uint32_t lo, uint32_t hi, int C, int row_elems, int lane,
+__device__ __forceinline__ void sample_issue_loads(Sample<NV, FT>& s, uint32_t lo, uint32_t hi, int C, int row_elems, int lane,
                                                    unsigned cmask) {
     constexpr int kE = Tap<FT>::kElems, kR = Tap<FT>::kRegs;
     static_assert(NV % kR == 0, "register vectors per tap must be a multiple of the registers one load fills");
@@ -308,22 +301,21 @@ __device__ __forceinline__ void sample_issue_loads(Sample<NV>& s, uint32_t lo, u
 #pragma unroll
         for (int l = 0; l < NV / kR; ++l) {
             if (cmask & (1u << l)) {
-                Tap<FT>::load(&s.t00[l * kR], p00 + l * 32 * kE);
-                Tap<FT>::load(&s.t01[l * kR], p00 + C + l * 32 * kE);
-                Tap<FT>::load(&s.t10[l * kR], p10 + l * 32 * kE);
-                Tap<FT>::load(&s.t11[l * kR], p10 + C + l * 32 * kE);
+                s.t00[l] = Tap<FT>::load(p00 + l * 32 * kE);
+                s.t01[l] = Tap<FT>::load(p00 + C + l * 32 * kE);
+                s.t10[l] = Tap<FT>::load(p10 + l * 32 * kE);
+                s.t11[l] = Tap<FT>::load(p10 + C + l * 32 * kE);
             }
         }
     } else {  // border sample: taps outside the map read as zero (Appendix A `tap(y,x)`)
 #pragma unroll
         for (int l = 0; l < NV / kR; ++l) {
             const bool cok = (cmask >> l) & 1u;
-#pragma unroll
-            for (int r = 0; r < kR; ++r) s.t00[l * kR + r] = s.t01[l * kR + r] = s.t10[l * kR + r] = s.t11[l * kR + r] = f4_zero();
-            if (cok && (flags & 1)) Tap<FT>::load(&s.t00[l * kR], p00 + l * 32 * kE);
-            if (cok && (flags & 2)) Tap<FT>::load(&s.t01[l * kR], p00 + C + l * 32 * kE);
-            if (cok && (flags & 4)) Tap<FT>::load(&s.t10[l * kR], p10 + l * 32 * kE);
-            if (cok && (flags & 8)) Tap<FT>::load(&s.t11[l * kR], p10 + C + l * 32 * kE);
+            s.t00[l] = s.t01[l] = s.t10[l] = s.t11[l] = Tap<FT>::zero();
+            if (cok && (flags & 1)) s.t00[l] = Tap<FT>::load(p00 + l * 32 * kE);
+            if (cok && (flags & 2)) s.t01[l] = Tap<FT>::load(p00 + C + l * 32 * kE);
+            if (cok && (flags & 4)) s.t10[l] = Tap<FT>::load(p10 + l * 32 * kE);
+            if (cok && (flags & 8)) s.t11[l] = Tap<FT>::load(p10 + C + l * 32 * kE);
         }
     }
 }
@@ -337,37 +329,44 @@ __device__ __forceinline__ unsigned channel_mask(int C, int lane) {
     return m;
 }
 
-template <int NV>
-__device__ __forceinline__ void sample_clear(Sample<NV>& s) {
+template <int NV, typename FT>
+__device__ __forceinline__ void sample_clear(Sample<NV, FT>& s) {
 #pragma unroll
-    for (int k = 0; k < NV; ++k) s.t00[k] = s.t01[k] = s.t10[k] = s.t11[k] = f4_zero();
+    for (int l = 0; l < NV / Tap<FT>::kRegs; ++l) s.t00[l] = s.t01[l] = s.t10[l] = s.t11[l] = Tap<FT>::zero();
 }
 
-template <int NV, bool FAST>
-__device__ __forceinline__ void sample_accum(float4 (&acc)[NV], const Sample<NV>& s) {
-#if SD3D_SCALAR_BLEND
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        acc[k].x = blend1<FAST>(acc[k].x, s.w00, s.w01, s.w10, s.w11, s.t00[k].x, s.t01[k].x, s.t10[k].x, s.t11[k].x);
-        acc[k].y = blend1<FAST>(acc[k].y, s.w00, s.w01, s.w10, s.w11, s.t00[k].y, s.t01[k].y, s.t10[k].y, s.t11[k].y);
-        acc[k].z = blend1<FAST>(acc[k].z, s.w00, s.w01, s.w10, s.w11, s.t00[k].z, s.t01[k].z, s.t10[k].z, s.t11[k].z);
-        acc[k].w = blend1<FAST>(acc[k].w, s.w00, s.w01, s.w10, s.w11, s.t00[k].w, s.t01[k].w, s.t10[k].w, s.t11[k].w);
-    }
-#else
+template <int NV, bool FAST, typename FT>
+__device__ __forceinline__ void sample_accum(float4 (&acc)[NV], const Sample<NV, FT>& s) {
+    constexpr int kR = Tap<FT>::kRegs;
+#if !SD3D_SCALAR_BLEND
     Weights2 w;
     w.w00 = pk2(s.w00, s.w00);
     w.w01 = pk2(s.w01, s.w01);
     w.w10 = pk2(s.w10, s.w10);
     w.w11 = pk2(s.w11, s.w11);
     w.one = pk2(c_one2.x, c_one2.y);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        blend2<FAST>(acc[k].x, acc[k].y, w, s.t00[k].x, s.t00[k].y, s.t01[k].x, s.t01[k].y, s.t10[k].x, s.t10[k].y,
-                     s.t11[k].x, s.t11[k].y);
-        blend2<FAST>(acc[k].z, acc[k].w, w, s.t00[k].z, s.t00[k].w, s.t01[k].z, s.t01[k].w, s.t10[k].z, s.t10[k].w,
-                     s.t11[k].z, s.t11[k].w);
-    }
 #endif
+#pragma unroll
+    for (int l = 0; l < NV / kR; ++l) {
+        float4 t00[kR], t01[kR], t10[kR], t11[kR];  // decoded here, when the loads have long been issued
+        Tap<FT>::decode(t00, s.t00[l]);
+        Tap<FT>::decode(t01, s.t01[l]);
+        Tap<FT>::decode(t10, s.t10[l]);
+        Tap<FT>::decode(t11, s.t11[l]);
+#pragma unroll
+        for (int r = 0; r < kR; ++r) {
+            float4& a = acc[l * kR + r];
+#if SD3D_SCALAR_BLEND
+            a.x = blend1<FAST>(a.x, s.w00, s.w01, s.w10, s.w11, t00[r].x, t01[r].x, t10[r].x, t11[r].x);
+            a.y = blend1<FAST>(a.y, s.w00, s.w01, s.w10, s.w11, t00[r].y, t01[r].y, t10[r].y, t11[r].y);
+            a.z = blend1<FAST>(a.z, s.w00, s.w01, s.w10, s.w11, t00[r].z, t01[r].z, t10[r].z, t11[r].z);
+            a.w = blend1<FAST>(a.w, s.w00, s.w01, s.w10, s.w11, t00[r].w, t01[r].w, t10[r].w, t11[r].w);
+#else
+            blend2<FAST>(a.x, a.y, w, t00[r].x, t00[r].y, t01[r].x, t01[r].y, t10[r].x, t10[r].y, t11[r].x, t11[r].y);
+            blend2<FAST>(a.z, a.w, w, t00[r].z, t00[r].w, t01[r].z, t01[r].w, t10[r].z, t10[r].w, t11[r].z, t11[r].w);
+#endif
+        }
+    }
 }
 
 // Appendix A lines `xc = ...` .. `w = ...` for one (point, view): returns zc, writes u / w

@@ -440,7 +440,7 @@ struct __align__(16) StageSlot {
 };
 
 template <int NV, typename FT>
-__device__ __forceinline__ void staged_issue(Sample<NV>& s, const uint4 r, const uint8_t* __restrict__ stage_ptr,
+__device__ __forceinline__ void staged_issue(Sample<NV, FT>& s, const uint4 r, const uint8_t* __restrict__ stage_ptr,
                                              const uint8_t* __restrict__ zero_ptr, const FT* __restrict__ fmap, int C,
                                              int row_elems, int lane, unsigned cmask) {
     constexpr int kR = Tap<FT>::kRegs;
@@ -456,13 +456,12 @@ __device__ __forceinline__ void staged_issue(Sample<NV>& s, const uint4 r, const
         const FT* __restrict__ g10 = g00 + row_elems;
 #pragma unroll
         for (int l = 0; l < NV / kR; ++l) {
-#pragma unroll
-            for (int j = 0; j < kR; ++j) s.t00[l * kR + j] = s.t01[l * kR + j] = s.t10[l * kR + j] = s.t11[l * kR + j] = f4_zero();
+            s.t00[l] = s.t01[l] = s.t10[l] = s.t11[l] = Tap<FT>::zero();
             const bool cok = (cmask >> l) & 1u;
-            if (cok && (r.y & 1u)) Tap<FT>::load(&s.t00[l * kR], g00 + l * 32 * kE);
-            if (cok && (r.y & 2u)) Tap<FT>::load(&s.t01[l * kR], g00 + C + l * 32 * kE);
-            if (cok && (r.y & 4u)) Tap<FT>::load(&s.t10[l * kR], g10 + l * 32 * kE);
-            if (cok && (r.y & 8u)) Tap<FT>::load(&s.t11[l * kR], g10 + C + l * 32 * kE);
+            if (cok && (r.y & 1u)) s.t00[l] = Tap<FT>::load(g00 + l * 32 * kE);
+            if (cok && (r.y & 2u)) s.t01[l] = Tap<FT>::load(g00 + C + l * 32 * kE);
+            if (cok && (r.y & 4u)) s.t10[l] = Tap<FT>::load(g10 + l * 32 * kE);
+            if (cok && (r.y & 8u)) s.t11[l] = Tap<FT>::load(g10 + C + l * 32 * kE);
         }
         return;
     }
@@ -479,17 +478,10 @@ __device__ __forceinline__ void staged_issue(Sample<NV>& s, const uint4 r, const
 #pragma unroll
     for (int l = 0; l < NV / kR; ++l) {
         if (cmask & (1u << l)) {
-            if constexpr (kR == 1) {
-                s.t00[l] = *reinterpret_cast<const float4*>(p00 + l * 512);
-                s.t01[l] = *reinterpret_cast<const float4*>(p01 + l * 512);
-                s.t10[l] = *reinterpret_cast<const float4*>(p10 + l * 512);
-                s.t11[l] = *reinterpret_cast<const float4*>(p11 + l * 512);
-            } else {
-                Tap<FT>::decode(&s.t00[l * kR], *reinterpret_cast<const uint4*>(p00 + l * 512));
-                Tap<FT>::decode(&s.t01[l * kR], *reinterpret_cast<const uint4*>(p01 + l * 512));
-                Tap<FT>::decode(&s.t10[l * kR], *reinterpret_cast<const uint4*>(p10 + l * 512));
-                Tap<FT>::decode(&s.t11[l * kR], *reinterpret_cast<const uint4*>(p11 + l * 512));
-            }
+            s.t00[l] = Tap<FT>::from_smem(p00 + l * 512);
+            s.t01[l] = Tap<FT>::from_smem(p01 + l * 512);
+            s.t10[l] = Tap<FT>::from_smem(p10 + l * 512);
+            s.t11[l] = Tap<FT>::from_smem(p11 + l * 512);
         }
     }
 }
@@ -664,9 +656,9 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
     const uint8_t* const lane_base = ring_ptr + lane * 16;
     const uint8_t* const zero_ptr = lane_base + (size_t)ring * rowb;
     float4 acc[PTS][NV];
-    Sample<NV> sa, sb;
-    sample_clear<NV>(sa);
-    if (DB) sample_clear<NV>(sb);
+    Sample<NV, FT> sa, sb;
+    sample_clear<NV, FT>(sa);
+    if (DB) sample_clear<NV, FT>(sb);
     int my_pid = -1, my_cnt = 0;  // lane t < PTS: the t-th point of this warp = point warp + WARPS * t of the run
     int run_start = 0, run_seg = -1, run_task = 0, red_n = 0;
     for (int n = 0;; ++n) {
@@ -718,14 +710,14 @@ __global__ void __launch_bounds__((32 / PTS + 1) * 32, 2)
                 if (t + 1 < PTS && ((wbits >> (WARPS * (t + 1))) & 1u))
                     staged_issue<NV, FT>((t & 1) ? sa : sb, S.rec[warp + WARPS * (t + 1)], stage_ptr, zero_ptr, fmap, p.C,
                                          row_elems, lane, cmask);
-                if ((wbits >> (WARPS * t)) & 1u) sample_accum<NV, FAST>(acc[t], (t & 1) ? sb : sa);
+                if ((wbits >> (WARPS * t)) & 1u) sample_accum<NV, FAST, FT>(acc[t], (t & 1) ? sb : sa);
             }
         } else {
 #pragma unroll
             for (int t = 0; t < PTS; ++t) {
                 if ((wbits >> (WARPS * t)) & 1u) {
                     staged_issue<NV, FT>(sa, S.rec[warp + WARPS * t], stage_ptr, zero_ptr, fmap, p.C, row_elems, lane, cmask);
-                    sample_accum<NV, FAST>(acc[t], sa);
+                    sample_accum<NV, FAST, FT>(acc[t], sa);
                 }
             }
         }

@@ -273,10 +273,9 @@ def measure_viewshard(wl: dict, exchange: str, steps: int, warmup: int, rank: in
     """Times `steps` view-sharded lifts of one scene of workload `wl` on `world` ranks (world == 1: the whole scene
     on this rank, no exchange). Every rank builds the same scene and keeps its contiguous view range. Device time
     with CUDA events, max over ranks. Returns (ms_per_step, n_superpoints, clocks)."""
-    from bench import ClockSampler
-    from .synth import make_scene
+    from bench import ClockSampler, build_scene
 
-    sc = make_scene(seed=1235, fmap_device=dev, **wl)  # identical on every rank (same seeds)
+    sc = build_scene(wl, 1235, fmap_device=dev)  # identical on every rank (same seeds)
     vb, ve = shard_range(wl["n_views"], world, rank)
     d = {k: getattr(sc, k).to(dev) for k in ("xyz", "sp_ids")}
     K_l = sc.K[vb:ve].contiguous().to(dev)

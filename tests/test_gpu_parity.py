@@ -812,3 +812,51 @@ def test_mask_logits_batched_one_launch(precision, tol):
     assert torch.equal(one[0], pred[0]) and torch.equal(one[1], attn[0])
     nothr, none = sd.mask_logits_batched([qs[0].to(DEV)], [mfs[0].to(DEV)], precision=precision)
     assert none is None and torch.equal(nothr[0], pred[0])
+
+
+@pytest.mark.parametrize("fmap_dtype", [torch.float16, torch.bfloat16])
+def test_full_size_scene_cfg3_16bit_maps_u16_depth(fmap_dtype):
+    """BASELINE configs[2]: the full-size scene with 16-bit DINO-X maps and ScanNet-native u16 depth, and the pooling
+    widths of that prototype (C = 32 SpConvUNet features, 96 = early fusion, 3 = coordinates;
+    configs/prototypes/SegDINO3D_ScanNetv2.py:15,25)."""
+    sc = make_scene(seed=1240, fmap_dtype=fmap_dtype)
+    depth = sc.depth_u16()
+    a, c, p, v = c_ref.lift_ref(sc.xyz, sc.K, sc.w2c, depth, sc.fmap, sc.stride)
+    feat_o = c_ref.finalize_ref(a, c)
+    sp_o = so.scatter_mean_oracle(feat_o, sc.sp_ids, dim=0)
+    d = sc.to(DEV)
+    feat, cnt, sp, plan = sd.lift_and_pool(d.xyz, d.K, d.w2c, depth.to(DEV), d.fmap, d.sp_ids, sc.n_superpoints)
+    assert torch.equal(cnt.cpu(), c) and torch.equal(feat.cpu(), feat_o) and rel_row_err(sp, sp_o) <= 1e-5
+    maps = sd.lift(d.xyz, d.K, d.w2c, depth.to(DEV), d.fmap, sc.stride, want_maps=True, plan=plan, variant=32768)
+    assert torch.equal(maps["pix_idx"].cpu(), p) and torch.equal(maps["vis"].cpu(), v)
+    assert torch.equal(maps["feat"], feat)  # the staged gather on the same inputs: same bits
+    g = torch.Generator().manual_seed(4)
+    for width in (32, 96, 3):
+        src = torch.randn(sc.xyz.shape[0], width, generator=g)
+        want = so.scatter_mean_oracle(src, sc.sp_ids, dim=0)
+        assert torch.equal(sd.scatter_mean(src.to(DEV), d.sp_ids, dim=0).cpu(), want), width
+        assert rel_row_err(sd.scatter_mean(src.to(DEV), d.sp_ids, dim=0, exact=False), want, floor=float(src.abs().mean())) <= 1e-5
+
+
+def test_large_scene_cfg4_shaped():
+    """BASELINE configs[3] shape, bounded: 1 M points, 64 views 640x480, ~5 k superpoints; the C restatement is the
+    checker. Integers bit-exact, features bit-exact (direct and staged gather), pooled features within 1e-5."""
+    sc = make_scene(n_points=1_000_000, n_views=64, seed=1301, sp_voxel=0.2, sp_target=5000)
+    assert 4500 <= sc.n_superpoints <= 5000
+    a, c, _, _ = c_ref.lift_ref(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride, want_maps=False)
+    feat_o = c_ref.finalize_ref(a, c)
+    sp_o = c_ref.scatter_mean_ref(feat_o, sc.sp_ids, sc.n_superpoints)
+    d = sc.to(DEV)
+    feat, cnt, sp, plan = sd.lift_and_pool(d.xyz, d.K, d.w2c, d.depth, d.fmap, d.sp_ids, sc.n_superpoints)
+    assert torch.equal(cnt.cpu(), c) and torch.equal(feat.cpu(), feat_o) and rel_row_err(sp, sp_o) <= 1e-5
+    perm, offs = so.sp_sort_oracle(sc.sp_ids, sc.n_superpoints)
+    assert torch.equal(plan.perm.cpu(), perm) and torch.equal(plan.seg_offsets[: sc.n_superpoints + 1].cpu(), offs)
+    staged = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan, pool=True, variant=32768)
+    assert torch.equal(staged["feat"], feat) and torch.equal(staged["count"], cnt)
+    assert rel_row_err(staged["sp_feat"], sp_o) <= 1e-5
+    # size-independent property: the view sum is additive over view ranges (what the multi-GPU split relies on)
+    first = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan, finalize=False, views=(0, 20))
+    rest = sd.lift(d.xyz, d.K, d.w2c, d.depth, d.fmap, sc.stride, plan=plan, finalize=False, views=(20, 64),
+                   accumulate_into=(first["feat"], first["count"]))
+    assert torch.equal(rest["count"], cnt)
+    assert torch.equal(sd.lift_finalize(rest["feat"], rest["count"]), feat)

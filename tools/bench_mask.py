@@ -35,3 +35,27 @@ for (n, s, d) in [(200, 500, 256), (500, 500, 256), (5000, 5000, 256)]:
         t = timeit(fn, 50 if n >= 5000 else 200)
         res[name] = {"us": t * 1e6, "tflops": flop / t / 1e12, "frac_of_bf16_peak": flop / t / 1e12 / PEAK_TF}
     print(json.dumps(res), flush=True)
+
+
+# a batch of 8 scenes at the decoder shape, with the attention-mask epilogue: ONE batched launch (row reset fused) against
+# the reference's per-scene sequence (einsum, sigmoid, compare, row sum, index_put: instance_seg_3d_decoder.py:557-573)
+def ref_head(qs, mfs):
+    out = []
+    for q, mf in zip(qs, mfs):
+        pm = torch.einsum("nd,md->nm", q, mf)
+        am = (pm.sigmoid() < 0.5).bool()
+        am[torch.where(am.sum(-1) == am.shape[-1])] = False
+        out.append((pm, am))
+    return out
+
+for b in (1, 8):
+    ops_ = [make_decoder_operands(200, 500, 256, seed=s_) for s_ in range(b)]
+    qs, mfs = [o[0].to(dev) for o in ops_], [o[1].to(dev) for o in ops_]
+    res = {"batch": b, "shape": [200, 500, 256]}
+    for name, fn in (("batched_tcgen05_bf16+attn", lambda: sd.mask_logits_batched(qs, mfs, precision="bf16", threshold=0.5)),
+                     ("batched_ffma_fp32+attn", lambda: sd.mask_logits_batched(qs, mfs, precision="fp32", threshold=0.5)),
+                     ("per_scene_tcgen05_bf16+attn", lambda: [sd.mask_logits(q, m, precision="bf16", threshold=0.5) for q, m in zip(qs, mfs)]),
+                     ("torch_reference_sequence", lambda: ref_head(qs, mfs))):
+        t = timeit(fn, 200)
+        res[name] = {"us": t * 1e6}
+    print(json.dumps(res), flush=True)

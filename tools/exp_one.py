@@ -7,7 +7,8 @@ from segdino3d_b200.synth import make_scene
 dev = torch.device("cuda:0")
 stride = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-sc = make_scene(seed=1235, stride=stride, fmap_device=dev).to(dev)
+kw = {"fmap_dtype": torch.float16} if len(sys.argv) > 3 and sys.argv[3] == "fp16" else {}
+sc = make_scene(seed=1235, stride=stride, fmap_device=dev, **kw).to(dev)
 for _ in range(6):
     plan = sd.sp_sort(sc.sp_ids, sc.n_superpoints, xyz=sc.xyz)
     r = sd.lift(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride, plan=plan, pool=True, variant=variant)
