@@ -436,6 +436,8 @@ def run_ours(args):
                        "parallelism": "scene replicas (no collective)" if world > 1 else "single GPU",
                        "l2": f"inputs rotate over {n_rot} distinct scenes ({n_rot * scene_mb} MB > 126 MB L2), no flush",
                        "run": args.run, "variant": args.variant, "streams": len(streams),
+                       "blend": "fma (<= 1e-5 of the oracle)" if args.variant & 1 else "unfused, bit-exact (Appendix A order)",
+                       "gather": "staged in shared memory (cp.async.bulk)" if args.variant & 32768 else "direct (LDG.128 tap rows)",
                        "projection_overlaps_plan": not args.no_overlap, "cuda_graph": bool(args.graph)},
             "points_per_s": value * n, "host_us_per_step": host_us,
             "roofline": {"bound": "hbm", "kernel": "gather_kernel (bilinear gather + view mean + run partials)",
@@ -471,7 +473,7 @@ def ncu_traffic(args):
     on (cfg2, default kernel), otherwise null."""
     import glob
     import re
-    if args.workload != "cfg2" or args.variant != 0 or args.run != 32:
+    if args.workload != "cfg2" or (args.variant & ~1) != 0 or args.run != 32:
         return None, "no ncu capture for this configuration"
     files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles",
                                           "r*_ncu_gather_summary.txt")))
@@ -497,7 +499,10 @@ def main():
     ap.add_argument("--exchange", default="reduce_scatter", choices=["allreduce", "reduce_scatter", "p2p"])
     ap.add_argument("--rotate", type=int, default=4, help="distinct scenes cycled through (defeats L2 residency)")
     ap.add_argument("--run", type=int, default=32, help="points per warp run")
-    ap.add_argument("--variant", type=int, default=0, help="points-per-warp group (0=default, 1/2/4/8)")
+    ap.add_argument("--variant", type=int, default=1,
+                    help="sd3d_lift variant bits (include/sd3d.h). Default 1 = bilinear blend contracted into FFMA: within "
+                         "the north star's 1e-5 of the oracle (tests: test_lift_fma_variant_*), integers still bit-exact; "
+                         "0 = the bit-exact unfused blend (Appendix A order); 32768 = shared-memory staged gather")
     ap.add_argument("--no-refine", action="store_true", help="skip the Morton refinement of the processing order")
     ap.add_argument("--streams", type=int, default=2, help="scenes kept in flight on separate CUDA streams")
     ap.add_argument("--graph", action="store_true",

@@ -3,8 +3,14 @@
  *
  * Boundary rules:
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
- *   - the caller (PyTorch) owns and allocates every buffer, including outputs and workspaces; the
- *     library never allocates, frees or retains a pointer past return;
+ *   - the caller (PyTorch) owns and allocates every buffer, including outputs and workspaces; the compute
+ *     entries never allocate, free or retain a pointer past return. Two documented exceptions, neither on the
+ *     per-scene path: sd3d_peer_alloc / sd3d_ipc_import hand out device memory the caller releases with
+ *     sd3d_peer_free / sd3d_ipc_close, and the library keeps a small pool of non-blocking side streams per device
+ *     (created on first use, never destroyed) on which sd3d_sp_plan and sd3d_lift_and_pool overlap independent
+ *     kernels; work on them is forked from and joined back into `stream` with events before the call returns;
+ *   - thread safety: entries are re-entrant; the only shared state is that stream pool (mutex) and per-device
+ *     once-flags for kernel attributes (atomics); sd3d_last_error() is thread-local;
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream);
  *   - every entry returns SD3D_OK or a negative code; sd3d_last_error() gives the thread-local text;
  *   - there is no CPU fallback: without a CUDA device every compute entry returns SD3D_ERR_CUDA.

@@ -10,13 +10,16 @@
 // deterministic function of (ids, xyz).
 //
 // Pipeline (all kernels tiny and latency-bound at ScanNet sizes, so the count of launches is what matters):
-//   radix pass = hist (per-block digit histogram, smem int atomics)
-//              -> scan (ONE CTA, whole bin-major [bins][blocks] matrix staged in shared memory)
-//              -> scatter (per-warp contiguous sub-chunks; __match_any_sync ranks keep equal keys in input
-//                 order; the last pass also emits a 27-bit Morton cell key per sorted point)
+//   radix pass = ONE cooperative kernel (radix_pass_fused_kernel): per-block digit histogram (smem int atomics)
+//              -> one grid.sync -> EVERY block reads the L2-resident [blocks][bins] matrix and derives its own column
+//                 prefix + the bin totals (no serial scan CTA, no second grid barrier)
+//              -> stable scatter (__match_any_sync ranks keep equal keys in input order; the last pass also emits a
+//                 27-bit Morton cell key per sorted point).
+//                 Fallback when the grid cannot be co-resident: three kernels hist / scan (one CTA) / scatter.
 //   one pass for S < 1024, ceil(log2(S+1)/10) passes otherwise (+ a boundary-search kernel).
 //   refine = per-superpoint stable LSD counting sort by the 27-bit cell key (one CTA per superpoint, <= 3 x 512 bins)
-//   tasks  = superpoints ranked along the world Morton curve, ceil(n_s/run) runs each (ONE CTA).
+//   tasks  = superpoints ranked along the world Morton curve, ceil(n_s/run) runs each (ONE CTA), launched on a
+//            library-owned side stream (plan_side_stream) so that it overlaps the refinement.
 // Keys outside [0,S) are mapped to the extra key S ("trash"), which sorts last.
 #include <cooperative_groups.h>
 

@@ -111,3 +111,69 @@ class PointFeatureLifter:
                                       z_near=self.z_near, strides=vw.get("strides"), order=plan)
             tgt["extra_features"]["points_2dfeats"] = feats[0] if len(feats) == 1 else ops.scale_mean(feats)
         return targets
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# registered drop-in classes (selected by `type=` in the reference's configs)
+# ---------------------------------------------------------------------------------------------------------------
+def register_dropins(registry_module=None):
+    """Registers ``SpConvUNetB200`` / ``Res16UNet34CB200`` / ``ScanNetQueryDecoderB200`` in the reference's mmengine
+    registries (segdino3d/builder.py:3-82), so that a config selects the sm_100a path with ``type='SpConvUNetB200'``
+    etc. -- same constructors, same forward signatures, same tensor layouts as the classes they derive from
+    (spconvunet.py:102, minkunet.py:692, decoder/instance_seg_3d_decoder.py:437).
+
+    * the backbones inherit ``forward_wrapper`` UNCHANGED; the module-level ``scatter_mean`` they call
+      (spconvunet.py:17, minkunet.py:16) is rebound to :func:`ops.scatter_mean` (CUDA tensors; CPU tensors keep the
+      original function, so dataset workers are unaffected);
+    * the decoder overrides only ``_forward_head`` (instance_seg_3d_decoder.py:532-577): heads as in the parent, the
+      einsum + attention-mask epilogue of :567-573 through one batched launch (:func:`forward_head_masks`).
+
+    Needs the reference package and its dependencies to be importable (mmengine, spconv, MinkowskiEngine); raises
+    ImportError otherwise. Returns the dict of registered classes."""
+    import importlib
+    builder = registry_module or importlib.import_module("segdino3d.builder")
+    sp_mod = importlib.import_module("segdino3d.models.backbone.spconvunet")
+    mk_mod = importlib.import_module("segdino3d.models.backbone.minkunet")
+    dec_mod = importlib.import_module("segdino3d.models.decoder.instance_seg_3d_decoder")
+
+    def _route(mod):
+        original = getattr(mod, "scatter_mean")
+        if getattr(original, "__sd3d_routed__", False):
+            return
+
+        def scatter_mean(src, index, dim=-1, out=None, dim_size=None):
+            if src.is_cuda:
+                return ops.scatter_mean(src, index, dim=dim, out=out, dim_size=dim_size)
+            return original(src, index, dim=dim, out=out, dim_size=dim_size)
+
+        scatter_mean.__sd3d_routed__ = True
+        mod.scatter_mean = scatter_mean
+
+    _route(sp_mod)
+    _route(mk_mod)
+
+    class SpConvUNetB200(sp_mod.SpConvUNet):
+        """SpConvUNet whose superpoint pooling runs on the sorted segmented-mean kernels (no global atomics)."""
+
+    class Res16UNet34CB200(mk_mod.Res16UNet34C):
+        """Res16UNet34C whose superpoint pooling runs on the sorted segmented-mean kernels."""
+
+    class ScanNetQueryDecoderB200(dec_mod.ScanNetQueryDecoder):
+        """ScanNetQueryDecoder whose mask logits + attention masks come from one batched kernel launch."""
+
+        mask_precision = "fp32"  # "bf16": tcgen05 tensor-core kernel (<= 1e-2)
+
+        def _forward_head(self, queries, mask_feats, last_flag):
+            norm = [self.out_norm(q) for q in queries]
+            cls_preds = [self.out_cls(nq) for nq in norm]
+            sem_preds = [self.out_sem(nq) for nq in norm] if last_flag else None
+            pred_scores = [self.out_score(nq) if self.objectness_flag else None for nq in norm]
+            thr = self.mask_attention_threshold if self.attn_mask else None
+            pred_masks, attn_masks = forward_head_masks(norm, list(mask_feats), thr, precision=self.mask_precision)
+            return cls_preds, sem_preds, pred_scores, pred_masks, attn_masks
+
+    builder.BACKBONES.register_module(module=SpConvUNetB200)
+    builder.BACKBONES.register_module(module=Res16UNet34CB200)
+    builder.DECODERS.register_module(module=ScanNetQueryDecoderB200)
+    return {"SpConvUNetB200": SpConvUNetB200, "Res16UNet34CB200": Res16UNet34CB200,
+            "ScanNetQueryDecoderB200": ScanNetQueryDecoderB200}

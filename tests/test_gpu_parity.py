@@ -315,6 +315,20 @@ def test_lift_fma_variant_within_tolerance():
     assert rel_row_err(r["feat"], lo.lift_finalize_oracle(a, c), floor=1.0) <= 1e-5
 
 
+@pytest.mark.parametrize("variant", [1, 32768 + 1])
+def test_lift_fma_variant_full_size_cfg2(variant):
+    """bench.py's default blend (variant bit 0, FFMA) at the full BASELINE configs[1] size, direct and staged gather:
+    count bit-exact, features and pooled features within the north star's 1e-5."""
+    sc = make_scene(seed=1236)
+    a, c, _, _ = c_ref.lift_ref(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.stride, want_maps=False)
+    feat_o = c_ref.finalize_ref(a, c)
+    sp_o = so.scatter_mean_oracle(feat_o, sc.sp_ids, dim=0)
+    d = sc.to(DEV)
+    feat, cnt, sp, _ = sd.lift_and_pool(d.xyz, d.K, d.w2c, d.depth, d.fmap, d.sp_ids, sc.n_superpoints, variant=variant)
+    assert torch.equal(cnt.cpu(), c)
+    assert rel_row_err(feat, feat_o, floor=1.0) <= 1e-5 and rel_row_err(sp, sp_o) <= 1e-5
+
+
 @pytest.mark.parametrize("channels", [64, 256, 512, 1024])
 @pytest.mark.parametrize("fmap_dtype", [torch.float16, torch.bfloat16])
 def test_lift_16bit_maps(fmap_dtype, channels):

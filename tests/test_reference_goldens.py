@@ -103,6 +103,51 @@ def test_bilinear_gather_against_grid_sample(stride):
     assert outside.any() and float(got[outside].abs().sum()) == 0.0  # all four taps outside -> exact zero
 
 
+def test_register_dropins_with_stand_in_reference_modules(monkeypatch):
+    """plugin.register_dropins against stand-ins of the reference modules (the real ones need mmengine / spconv / ME):
+    the three classes land in the registries under their `type=` names, CPU tensors keep the original scatter_mean,
+    and the decoder override returns the 5-tuple of _forward_head with the parent's heads."""
+    import types
+    from segdino3d_b200 import plugin
+
+    class Registry:
+        def __init__(self):
+            self.modules = {}
+
+        def register_module(self, module=None):
+            self.modules[module.__name__] = module
+            return module
+
+    calls = []
+
+    def cpu_scatter_mean(src, index, dim=-1, out=None, dim_size=None):
+        calls.append("original")
+        return so.scatter_mean_oracle(src, index, dim=dim, dim_size=dim_size)
+
+    class Decoder:  # stand-in for ScanNetQueryDecoder: only what _forward_head touches
+        def __init__(self):
+            self.out_norm = torch.nn.LayerNorm(8)
+            self.out_cls, self.out_sem, self.out_score = torch.nn.Linear(8, 3), torch.nn.Linear(8, 4), torch.nn.Linear(8, 1)
+            self.objectness_flag, self.attn_mask, self.mask_attention_threshold = True, True, 0.5
+
+    builder = types.SimpleNamespace(BACKBONES=Registry(), DECODERS=Registry())
+    mods = {"segdino3d.builder": builder,
+            "segdino3d.models.backbone.spconvunet": types.SimpleNamespace(SpConvUNet=type("SpConvUNet", (), {}), scatter_mean=cpu_scatter_mean),
+            "segdino3d.models.backbone.minkunet": types.SimpleNamespace(Res16UNet34C=type("Res16UNet34C", (), {}), scatter_mean=cpu_scatter_mean),
+            "segdino3d.models.decoder.instance_seg_3d_decoder": types.SimpleNamespace(ScanNetQueryDecoder=Decoder)}
+    import importlib
+    monkeypatch.setattr(importlib, "import_module", lambda name: mods[name])
+    classes = plugin.register_dropins()
+    assert set(builder.BACKBONES.modules) == {"SpConvUNetB200", "Res16UNet34CB200"}
+    assert set(builder.DECODERS.modules) == {"ScanNetQueryDecoderB200"}
+    routed = mods["segdino3d.models.backbone.spconvunet"].scatter_mean
+    out = routed(torch.ones(4, 2), torch.tensor([0, 0, 1, 1]), dim=0)  # CPU tensors: the original implementation
+    assert calls == ["original"] and out.shape == (2, 2)
+    plugin.register_dropins()  # idempotent: the routed function is not wrapped twice
+    assert mods["segdino3d.models.backbone.spconvunet"].scatter_mean is routed
+    assert issubclass(classes["ScanNetQueryDecoderB200"], Decoder)
+
+
 # ------------------------------------------------------------------------------------------------------
 # the CUDA path against the reference-executed vectors
 # ------------------------------------------------------------------------------------------------------
@@ -134,3 +179,47 @@ def test_cuda_mask_head_reproduces_reference_forward_head(ref):
         decided = want.abs() > 1e-4 * scale  # logits within rounding distance of the threshold may fall either side
         assert torch.equal(attn[i].cpu()[decided], ref[f"head_attn{i}"].bool()[decided])
     assert not attn[1][3].any()  # the all-true row is reset (instance_seg_3d_decoder.py:570-571)
+
+
+@pytest.mark.gpu
+def test_registered_decoder_dropin_forward_head(ref):
+    """ScanNetQueryDecoderB200._forward_head (stand-in parent with the reference's head attributes) on the golden
+    inputs == the reference text's outputs."""
+    import types
+    import importlib
+    from segdino3d_b200 import plugin
+
+    class Registry:
+        def register_module(self, module=None):
+            return module
+
+    class Decoder:
+        def __init__(self):
+            self.out_norm = torch.nn.LayerNorm(256).to(DEV)
+            with torch.no_grad():
+                self.out_norm.weight.copy_(ref["head_ln_weight"])
+                self.out_norm.bias.copy_(ref["head_ln_bias"])
+            self.out_cls = self.out_sem = self.out_score = lambda x: x[:, :1]
+            self.objectness_flag, self.attn_mask, self.mask_attention_threshold = True, True, 0.5
+
+    mods = {"segdino3d.builder": types.SimpleNamespace(BACKBONES=Registry(), DECODERS=Registry()),
+            "segdino3d.models.backbone.spconvunet": types.SimpleNamespace(SpConvUNet=object, scatter_mean=lambda *a, **k: None),
+            "segdino3d.models.backbone.minkunet": types.SimpleNamespace(Res16UNet34C=object, scatter_mean=lambda *a, **k: None),
+            "segdino3d.models.decoder.instance_seg_3d_decoder": types.SimpleNamespace(ScanNetQueryDecoder=Decoder)}
+    real = importlib.import_module
+    importlib.import_module = lambda name: mods[name] if name in mods else real(name)
+    try:
+        dec = plugin.register_dropins()["ScanNetQueryDecoderB200"]()
+    finally:
+        importlib.import_module = real
+    with torch.no_grad():
+        cls_p, sem_p, scores, pred, attn = dec._forward_head([ref[f"head_q{i}"].to(DEV) for i in range(2)],
+                                                             [ref[f"head_mf{i}"].to(DEV) for i in range(2)], True)
+    assert len(cls_p) == len(sem_p) == len(scores) == 2
+    for i in range(2):
+        want = ref[f"head_pred{i}"]
+        scale = want.abs().amax(dim=1, keepdim=True).clamp(min=1.0)
+        assert float(((pred[i].cpu() - want).abs() / scale).max()) <= 2e-5  # LayerNorm on the GPU + the fp32 kernel
+        decided = want.abs() > 1e-3 * scale
+        assert torch.equal(attn[i].cpu()[decided], ref[f"head_attn{i}"].bool()[decided])
+    assert not attn[1][3].any()
