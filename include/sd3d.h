@@ -218,6 +218,23 @@ int sd3d_mask_logits_batched(const float* const* q_host, const float* const* mf_
                              const int* S_host, int count, int d, int precision, float* const* out_host, float thr,
                              uint8_t* const* attn_host /*nullable*/, void* stream);
 
+/* Operand producer of the mask head: y = LayerNorm(x) * weight + bias over the last dimension
+ *   (self.out_norm(queries[i]), instance_seg_3d_decoder.py:558), written in ONE pass as fp32 (y_f32: what the cls /
+ *   sem / score heads read, :561-566) and / or bf16 (y_bf16: the tensor-core operand). normalize == 0: no
+ *   normalisation (weight / bias still applied when given) = the cast of the x_mask MLP output (:261-263, :645).
+ *   x[n,d] f32 row-major, d <= 1024; weight / bias [d] nullable; y_f32 [n,d] / y_bf16 [n,d] nullable (not both). */
+int sd3d_layernorm_cast(const float* x, const float* weight, const float* bias, int n, int d, float eps, int normalize,
+                        float* y_f32, void* y_bf16, void* stream);
+
+/* The same contraction on bf16 operands fed by TMA tensor loads (cp.async.bulk.tensor, 128-byte swizzle) into
+ *   tcgen05.mma 128 x 128 x 16 tiles, persistent CTAs, warp-specialised (TMA / MMA / epilogue):
+ *   q_bf16[n,d], mf_bf16[S,d] row-major bf16 (d % 64 == 0, d <= 256, 16-byte aligned), out[n,S] f32,
+ *   attn_mask nullable as in sd3d_mask_logits; ws: sd3d_mask_logits_bf16_workspace_bytes(n) bytes of row flags
+ *   (only read when attn_mask != NULL). Logits within 1e-2 of the fp32 einsum (bf16 operands, fp32 accumulate). */
+size_t sd3d_mask_logits_bf16_workspace_bytes(int n);
+int sd3d_mask_logits_bf16(const void* q_bf16, const void* mf_bf16, int n, int S, int d, float* out, float thr,
+                          uint8_t* attn_mask, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * "next" rows of SURVEY 8(f)
  * --------------------------------------------------------------------------------------------- */

@@ -63,6 +63,10 @@ SYMBOLS = {
     "sd3d_sp_expand_mask": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_float, c_void_p, c_void_p, c_void_p]),
     "sd3d_sp_label_vote": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p]),
     "sd3d_sp_mean_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "sd3d_layernorm_cast": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p, c_void_p]),
+    "sd3d_mask_logits_bf16_workspace_bytes": (c_size_t, [c_int]),
+    "sd3d_mask_logits_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p,
+                                      c_size_t, c_void_p]),
     "sd3d_mask_logits_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float,
                                          c_void_p, c_void_p]),
     "sd3d_mask_logits": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p,

@@ -631,11 +631,66 @@ def lift_and_pool(xyz, K, pose_w2c, depth, fmap, sp_ids: torch.Tensor, n_superpo
 # ---------------------------------------------------------------------------------------------------
 # mask logits
 # ---------------------------------------------------------------------------------------------------
+def layernorm_cast(x: torch.Tensor, weight: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                   eps: float = 1e-5, normalize: bool = True, want_f32: bool = True, want_bf16: bool = True):
+    """The operand producer of the mask head in one pass: ``LayerNorm(x)`` (``self.out_norm``,
+    instance_seg_3d_decoder.py:558) as fp32 (for the cls / sem / score heads) and / or bf16 (tensor-core operand);
+    ``normalize=False`` = plain cast (the ``x_mask`` output, :261-263). Returns (y_f32 or None, y_bf16 or None)."""
+    _need_cuda("x", x)
+    if x.dim() != 2 or x.dtype != torch.float32:
+        raise ValueError("x must be float32 [n, d]")
+    x = x.contiguous()
+    n, d = x.shape
+    with torch.cuda.device(x.device):
+        y32 = torch.empty_like(x) if want_f32 else None
+        y16 = torch.empty(n, d, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+        check(_lib.load().sd3d_layernorm_cast(_ptr(x), _ptr(weight.contiguous() if weight is not None else None),
+                                              _ptr(bias.contiguous() if bias is not None else None), n, d, float(eps),
+                                              1 if normalize else 0, _ptr(y32), _ptr(y16), _stream()), "sd3d_layernorm_cast")
+    return y32, y16
+
+
+def mask_logits_bf16(q_bf16: torch.Tensor, mf_bf16: torch.Tensor, threshold: Optional[float] = None):
+    """``einsum('nd,md->nm')`` on bf16 operands through the TMA-fed tcgen05 kernel (``sd3d_mask_logits_bf16``):
+    out [n,S] float32 (+ bool attention mask with ``threshold``). d % 64 == 0, d <= 256."""
+    _need_cuda("q", q_bf16)
+    _need_cuda("mf", mf_bf16)
+    if q_bf16.dtype != torch.bfloat16 or mf_bf16.dtype != torch.bfloat16 or q_bf16.dim() != 2 or mf_bf16.dim() != 2 \
+            or q_bf16.shape[1] != mf_bf16.shape[1]:
+        raise ValueError("need bfloat16 [n,d] x [S,d]")
+    q_bf16, mf_bf16 = q_bf16.contiguous(), mf_bf16.contiguous()
+    n, d = q_bf16.shape
+    s = mf_bf16.shape[0]
+    dev = q_bf16.device
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        out = torch.empty(n, s, dtype=torch.float32, device=dev)
+        attn = torch.empty(n, s, dtype=torch.uint8, device=dev) if threshold is not None else None
+        ws_bytes = int(lib.sd3d_mask_logits_bf16_workspace_bytes(n)) if threshold is not None else 0
+        ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev) if threshold is not None else None
+        check(lib.sd3d_mask_logits_bf16(_ptr(q_bf16), _ptr(mf_bf16), n, s, d, _ptr(out),
+                                        float(threshold) if threshold is not None else 0.0, _ptr(attn), _ptr(ws), ws_bytes,
+                                        _stream()), "sd3d_mask_logits_bf16")
+    return (out, attn.view(torch.bool)) if threshold is not None else out
+
+
+_TMA_MIN_TILES = 64  # below this many 128 x 128 output tiles the register-staged kernel (one launch, no casts) wins
+
+
 def _mask_logits_raw(q: torch.Tensor, mf: torch.Tensor, code: int, threshold: Optional[float]):
     """One ``sd3d_mask_logits`` call on contiguous float32 CUDA operands: out[n,S] (+ uint8 attention mask)."""
     n, d = q.shape
     s = mf.shape[0]
     dev = q.device
+    if code == _lib.BF16 and d % 64 == 0 and d <= 256 and ((n + 127) // 128) * ((s + 127) // 128) >= _TMA_MIN_TILES:
+        # large problem: cast the operands once (what a fused LayerNorm / x_mask epilogue would hand over), then the
+        # TMA-fed kernel
+        _, q16 = layernorm_cast(q, normalize=False, want_f32=False)
+        _, mf16 = layernorm_cast(mf, normalize=False, want_f32=False)
+        res = mask_logits_bf16(q16, mf16, threshold)
+        if threshold is None:
+            return res, None
+        return res[0], res[1].view(torch.uint8)
     with torch.cuda.device(dev):
         out = torch.empty(n, s, dtype=torch.float32, device=dev)
         attn = torch.empty(n, s, dtype=torch.uint8, device=dev) if threshold is not None else None

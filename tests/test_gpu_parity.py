@@ -874,3 +874,47 @@ def test_large_scene_cfg4_shaped():
                    accumulate_into=(first["feat"], first["count"]))
     assert torch.equal(rest["count"], cnt)
     assert torch.equal(sd.lift_finalize(rest["feat"], rest["count"]), feat)
+
+
+# ----------------------------------------------------------------------------------------------------
+# TMA-fed tcgen05 mask GEMM + its operand producer
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d", [(200, 256), (37, 64), (1, 1000), (513, 128)])
+def test_layernorm_cast_producer(n, d):
+    """self.out_norm(queries) (instance_seg_3d_decoder.py:558) as fp32 + bf16 in one pass, and the plain cast."""
+    g = torch.Generator().manual_seed(n + d)
+    x = torch.randn(n, d, generator=g) * 3 + 0.7
+    w, b = 1 + 0.1 * torch.randn(d, generator=g), 0.05 * torch.randn(d, generator=g)
+    want = torch.nn.functional.layer_norm(x, (d,), w, b, 1e-5)
+    y32, y16 = sd.layernorm_cast(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5)
+    assert float((y32.cpu() - want).abs().max()) <= 2e-6 * float(want.abs().max())
+    assert torch.equal(y16.cpu(), y32.cpu().to(torch.bfloat16))
+    _, c16 = sd.layernorm_cast(x.to(DEV), normalize=False, want_f32=False)
+    assert torch.equal(c16.cpu(), x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("n,s,d", [(5000, 5000, 256), (300, 700, 256), (129, 1023, 64), (1, 130, 128), (1000, 2053, 192)])
+def test_mask_logits_bf16_tma_kernel(n, s, d):
+    """TMA tensor loads -> tcgen05 128x128x16 -> TMEM epilogue. Exact (<= 1e-5) against the fp32 product of the
+    bf16-rounded operands, <= 1e-2 against the fp32 einsum; attention mask incl. all-true rows; tile / row-block
+    remainders, S not a multiple of 4, persistent CTAs spanning several row blocks."""
+    g = torch.Generator().manual_seed(n + s)
+    q = torch.nn.functional.layer_norm(torch.randn(n, d, generator=g), (d,))
+    mf = 0.3 * torch.randn(s, d, generator=g)
+    row = min(5, n - 1)
+    mf = mf - 0.25 * q[row][None, :]  # query `row`: every logit negative (mean -0.25 d, sd 0.3 sqrt(d)) -> all-true row
+    q16, mf16 = q.to(torch.bfloat16), mf.to(torch.bfloat16)
+    pred, attn = sd.mask_logits_bf16(q16.to(DEV), mf16.to(DEV), threshold=0.5)
+    exact = mo.mask_logits_f64(q16.float(), mf16.float()).float()
+    scale = exact.abs().amax(dim=1, keepdim=True).clamp(min=1.0)
+    assert float(((pred.cpu() - exact).abs() / scale).max()) <= 1e-5
+    assert float(((pred.cpu() - mo.mask_logits_oracle(q, mf)).abs() / scale).max()) <= 1e-2
+    mine = pred.cpu()
+    assert torch.equal(attn.cpu(), mo.attn_mask_oracle(mine, 0.5)) or \
+        torch.equal(attn.cpu()[mine.abs().amin(dim=1) > 1e-6], mo.attn_mask_oracle(mine, 0.5)[mine.abs().amin(dim=1) > 1e-6])
+    assert not attn[row].any() and bool((mine[row] < 0).all())
+    nothr = sd.mask_logits_bf16(q16.to(DEV), mf16.to(DEV))
+    assert torch.equal(nothr, pred)
+    if n * s >= 1_000_000:  # the public entry routes large bf16 problems here (after casting the fp32 operands)
+        via = sd.mask_logits(q.to(DEV), mf.to(DEV), precision="bf16", threshold=0.5)
+        assert torch.equal(via[0], pred) and torch.equal(via[1], attn)

@@ -27,7 +27,11 @@ for (n, s, d) in [(200, 500, 256), (500, 500, 256), (5000, 5000, 256)]:
     q, mf = q.to(dev), mf.to(dev)
     flop = 2.0 * n * s * d
     res = {"shape": [n, s, d], "flop": flop}
-    for name, fn in (("tcgen05_bf16", lambda: sd.mask_logits(q, mf, precision="bf16")),
+    _, q16 = sd.layernorm_cast(q, normalize=False, want_f32=False)
+    _, mf16 = sd.layernorm_cast(mf, normalize=False, want_f32=False)
+    for name, fn in (("tma_tcgen05_bf16_operands", lambda: sd.mask_logits_bf16(q16, mf16)),
+                     ("tma_tcgen05_bf16_operands+attn_mask", lambda: sd.mask_logits_bf16(q16, mf16, threshold=0.5)),
+                     ("tcgen05_bf16", lambda: sd.mask_logits(q, mf, precision="bf16")),
                      ("tcgen05_bf16+attn_mask", lambda: sd.mask_logits(q, mf, precision="bf16", threshold=0.5)),
                      ("ffma_fp32", lambda: sd.mask_logits(q, mf, precision="fp32")),
                      ("torch_einsum_fp32", lambda: torch.einsum("nd,md->nm", q, mf)),

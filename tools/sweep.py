@@ -39,7 +39,7 @@ for cs in cases:
             sc = scenes[i % n_rot]
             with torch.cuda.stream(streams[i % 2]):
                 sd.lift_and_pool(sc.xyz, sc.K, sc.w2c, sc.depth, sc.fmap, sc.sp_ids, sc.n_superpoints, stride=sc.stride,
-                                 events=None if evs is None else evs[i])
+                                 variant=1, events=None if evs is None else evs[i])
         for s_ in streams: torch.cuda.current_stream().wait_stream(s_)
     run(4); torch.cuda.synchronize()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -47,7 +47,7 @@ for cs in cases:
     a.record(); run(K, evs); b.record(); torch.cuda.synchronize()
     step_ms = a.elapsed_time(b) / K
     gather_ms = sum(x.elapsed_time(y) for x, y in evs) / K
-    b_gather = v * hf * wf * c * sf + n * ((v + 31) // 32) * 4 + n * 12 + v * 64 + n * c * 4 + n * 4
+    b_gather = v * hf * wf * c * sf + n * c * 4 + n * 12  # compulsory bytes of what the gather kernel touches
     b_path = v * (hf * wf * c * sf + 480 * 640 * 4) + n * 12 + v * 64 + n * c * 4 + n * 4 + n * 8 + scenes[0].n_superpoints * c * 4
     cnt = sd.lift(scenes[0].xyz, scenes[0].K, scenes[0].w2c, scenes[0].depth, scenes[0].fmap, scenes[0].stride)["count"]
     print(json.dumps({"n_points": n, "n_views": v, "stride": st, "channels": c, "fmap_dtype": str(cs["dtype"]).split(".")[1],
