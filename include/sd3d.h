@@ -235,6 +235,17 @@ size_t sd3d_mask_logits_bf16_workspace_bytes(int n);
 int sd3d_mask_logits_bf16(const void* q_bf16, const void* mf_bf16, int n, int S, int d, float* out, float thr,
                           uint8_t* attn_mask, void* ws, size_t ws_bytes, void* stream);
 
+/* fp32-level accuracy on the same tensor-core kernel ("bf16x3"): every fp32 operand element is split into
+ *   hi = bf16(x), mid = bf16(x - hi)  (sd3d_split_bf16: x[n,d] f32 -> y[n,2d] bf16 = (hi | mid), d % 4 == 0), and
+ *   out = hi.hi + hi.mid + mid.hi accumulated in fp32. The dropped terms are <= 2^-16 relative per product; measured
+ *   against the float64 product the result is within 2e-6 of |q||mf| (the cuBLAS fp32 einsum: 3e-7), i.e. inside the
+ *   1e-5 tolerance of the path. Same shapes / workspace / attention-mask contract as sd3d_mask_logits_bf16, with
+ *   q_split[n,2d], mf_split[S,2d]. Replaces the FFMA path of sd3d_mask_logits for large problems
+ *   (instance_seg_3d_decoder.py:567 at eval scale: the reference runs this einsum in fp32, amp=False). */
+int sd3d_split_bf16(const float* x, int n, int d, void* y_split, void* stream);
+int sd3d_mask_logits_bf16x3(const void* q_split, const void* mf_split, int n, int S, int d, float* out, float thr,
+                            uint8_t* attn_mask, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * "next" rows of SURVEY 8(f)
  * --------------------------------------------------------------------------------------------- */

@@ -6,14 +6,25 @@
 //
 // mask_gemm.cu stages fp32 operands through registers (LDG + cvt + swizzled STS in every CTA): at 5000 x 5000 x 256 that
 // staging and the 100 MB fp32 output bound it (9 % of the bf16 peak). Here the operands are bf16 in HBM, so
-//   * warp 0   issues cp.async.bulk.tensor.2d (TMA, SWIZZLE_128B boxes of 128 rows x 64 bf16) straight into the canonical
-//              K-major layout the UMMA descriptors expect: no load / convert / store instructions at all;
-//   * warp 1   issues tcgen05.mma.cta_group::1.kind::f16 M=128, N=128, K=16 (d/16 per tile) into one of two TMEM stages
-//              and commits to the mbarriers that free the B stage and publish the accumulator;
-//   * warps 2-5 read the accumulator with tcgen05.ld (each warp its lane quarter), write the fp32 logits with 128-bit
-//              stores and the thresholded mask bytes, and track all-true rows.
-// Persistent CTAs (one per SM, 192 KB of shared memory): CTA c owns a contiguous range of the linear tile index
+//   * warp 0   issues cp.async.bulk.tensor.2d (TMA, SWIZZLE_128B boxes of 128 / 256 rows x 64 bf16) straight into the
+//              canonical K-major layout the UMMA descriptors expect: no load / convert / store instructions at all;
+//   * warp 1   issues tcgen05.mma.cta_group::1.kind::f16 M=128, N=256 (bf16) or 128 (bf16x3), K=16 into one of two TMEM
+//              accumulator stages and commits to the mbarriers that free the B ring slot and publish the accumulator;
+//   * warps 2-9 are two epilogue groups, one per TMEM stage (tiles alternate between them): each warp reads its lane
+//              quarter with tcgen05.ld, stages 32 x 32 fp32 blocks in shared memory and stores them with
+//              cp.async.bulk.tensor (full 128-byte lines), writes the thresholded mask bytes and tracks all-true rows.
+// Persistent CTAs (one per SM, 225 KB of shared memory): CTA c owns a contiguous range of 128-column half tiles
 // (row block major), reloading the 128 x d A block only when the row block changes.
+//
+// What was measured while shaping it (5000 x 5000 x 256, ncu kernel times, debug builds that switched parts off):
+//   * the synchronisation skeleton alone (no loads, MMAs, tcgen05.ld, stores) cost 1.1 us per 128 x 128 tile: the MMA
+//     thread pays ~60 cycles per tcgen05.mma issue and ~200 per tcgen05.commit (clock64 around the issue block), i.e.
+//     more than the 64 tensor cycles of an N = 128 instruction -> N = 256 instructions (half the issues per flop):
+//     front end 24.6 -> 17.6 us; ring depth (2..8 K blocks in flight), polling vs try_wait, converged vs single-lane
+//     producer / issuer warps, 4 vs 8 epilogue warps made no difference;
+//   * TMA loads of B are not the limit (skipping them: -0.4 us); the output path adds ~8 us on top of the front end
+//     (shared-memory bandwidth: MMA operand reads + TMA-in + staging write + TMA-store read ~ 4.5 k cycles per 128 x 256
+//     tile); plain 16-byte-per-lane stores instead of the TMA store: 46 us.
 #include <cuda.h>
 
 #include <cmath>
@@ -22,8 +33,11 @@
 
 namespace sd3d {
 
-constexpr int kTmBM = 128, kTmBN = 128, kTmKB = 64;  // tile rows / columns, bf16 elements per 128-byte swizzle row
-constexpr int kTmThreads = 192;                       // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kTmBM = 128, kTmKB = 64;  // tile rows, bf16 elements per 128-byte swizzle row
+// tile columns = N of one tcgen05.mma: 256 for bf16 (one MMA issue + commit costs the issuing thread ~60 / ~200 cycles,
+// measured; at N = 128 that alone exceeds the 64 tensor cycles of the instruction), 128 for bf16x3 (shared memory)
+constexpr int tm_bn(bool split) { return split ? 128 : 256; }
+constexpr int kTmThreads = 320;                       // warp 0 TMA, warp 1 MMA, warps 2..5 / 6..9 epilogue of TMEM stage 0 / 1
 constexpr int kTmStages = 2;
 constexpr int kTmSlab = kTmBM * 128;                  // one K block of a 128-row operand tile: 16 KB
 
@@ -58,6 +72,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tm_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100: version 1 at bit 46, layout type 2 at 61)
 __device__ __forceinline__ uint64_t tm_desc(uint32_t smem_addr) {
     uint64_t desc = 0;
@@ -69,28 +92,56 @@ __device__ __forceinline__ uint64_t tm_desc(uint32_t smem_addr) {
     return desc;
 }
 
+// A block (128 rows x d) resident in shared memory; B streams through a ring of K-block steps (one step = the 64-wide
+// K block kb of a tile, ring_steps steps in flight), so that shared memory is left for double-buffered epilogue staging.
+// SPLIT = false: operands are [rows, d] bf16; a step is 256 rows x 64 of mf (32 KB, one TMA box).
+// SPLIT = true ("bf16x3", fp32-level accuracy): operands are [rows, 2d] bf16 = (hi | mid) with hi = bf16(x),
+// mid = bf16(x - hi); out = hi.mid + mid.hi + hi.hi accumulated in the fp32 TMEM accumulator (the dropped terms are
+// <= 2^-16 relative per product). Both halves of the A block stay resident; a step is the (hi, mid) slab pair of 128 rows.
+//
+// Work is dealt out in 128-column half tiles (row-block major): CTA c owns half tiles [c * halves_per_cta, ...). An even
+// half tile and its successor (same row block, same CTA) are processed as ONE 128 x 256 tile (N = 256 MMAs), the
+// rest as 128 x 128 tiles (the same 256-row TMA box, N = 128 in the instruction descriptor): full-width MMAs where
+// possible and a makespan quantised in half tiles.
+constexpr int kTmMaxRing = 4;
+
+struct TmTile {
+    int mb, col0, width;
+};
+__device__ __forceinline__ TmTile tm_next_tile(int64_t& h, int64_t h_end, int n_half, int bn) {
+    const int mb = (int)(h / n_half), hb = (int)(h % n_half);
+    const int halves = (bn == 256 && (hb & 1) == 0 && h + 1 < h_end && hb + 1 < n_half) ? 2 : 1;
+    h += halves;
+    return TmTile{mb, hb * 128, halves * 128};
+}
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(kTmThreads, 1)
     mask_logits_tma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_mf,
                            const __grid_constant__ CUtensorMap map_out, int tma_store, int n, int S, int d,
-                           int tiles_per_cta, float* __restrict__ out, float thr, uint8_t* __restrict__ attn,
-                           int32_t* __restrict__ row_false) {
+                           int halves_per_cta, int ring_steps, int epi_bufs, float* __restrict__ out, float thr,
+                           uint8_t* __restrict__ attn, int32_t* __restrict__ row_false) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int kblocks = d / kTmKB;
-    uint8_t* sA = smem;                                   // kblocks slabs
-    uint8_t* sB = smem + (size_t)kblocks * kTmSlab;       // kTmStages x kblocks slabs
-    uint8_t* sEpi = sB + (size_t)kTmStages * kblocks * kTmSlab;  // 4 epilogue warps x 2 buffers x [32 rows][128 B] (swizzled)
-    __shared__ __align__(8) uint64_t s_bar[2 + 4 * kTmStages];  // a_full, a_free, b_full[2], b_free[2], acc_full[2], acc_free[2]
+    constexpr int kTmBN = tm_bn(SPLIT);
+    constexpr int kStepSlabs = 2;  // bf16: 256 rows of one K block; bf16x3: the (hi, mid) slabs of 128 rows
+    const int a_slabs = SPLIT ? 2 * kblocks : kblocks;    // resident A block
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)a_slabs * kTmSlab;       // ring_steps steps
+    uint8_t* sEpi = sB + (size_t)ring_steps * kStepSlabs * kTmSlab;  // 8 epilogue warps x epi_bufs x [32 rows][128 B] (swizzled)
+    // a_full, a_free, b_full[ring], b_free[ring], acc_full[2], acc_free[2]
+    __shared__ __align__(8) uint64_t s_bar[2 + 2 * kTmMaxRing + 2 * kTmStages];
     __shared__ uint32_t s_tmem;
     const uint32_t a_full = tm_smem(&s_bar[0]), a_free = tm_smem(&s_bar[1]);
-    const uint32_t b_full = tm_smem(&s_bar[2]), b_free = tm_smem(&s_bar[2 + kTmStages]);
-    const uint32_t acc_full = tm_smem(&s_bar[2 + 2 * kTmStages]), acc_free = tm_smem(&s_bar[2 + 3 * kTmStages]);
+    const uint32_t b_full = tm_smem(&s_bar[2]), b_free = tm_smem(&s_bar[2 + kTmMaxRing]);
+    const uint32_t acc_full = tm_smem(&s_bar[2 + 2 * kTmMaxRing]), acc_free = tm_smem(&s_bar[2 + 2 * kTmMaxRing + kTmStages]);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = (S + kTmBN - 1) / kTmBN, m_blocks = (n + kTmBM - 1) / kTmBM;
-    const int64_t total = (int64_t)n_tiles * m_blocks;
-    const int64_t t_begin = (int64_t)blockIdx.x * tiles_per_cta;
-    const int64_t t_end = t_begin + tiles_per_cta < total ? t_begin + tiles_per_cta : total;
+    const int n_half = (S + 127) / 128, m_blocks = (n + kTmBM - 1) / kTmBM;
+    const int64_t total = (int64_t)n_half * m_blocks;
+    const int64_t h_begin = (int64_t)blockIdx.x * halves_per_cta;
+    const int64_t h_end = h_begin + halves_per_cta < total ? h_begin + halves_per_cta : total;
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tm_smem(&s_tmem)),
@@ -99,9 +150,9 @@ __global__ void __launch_bounds__(kTmThreads, 1)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 + 3 * kTmStages; ++i)
+        for (int i = 0; i < 2 + 2 * kTmMaxRing + kTmStages; ++i)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tm_smem(&s_bar[i])) : "memory");
-        for (int i = 0; i < kTmStages; ++i)  // accumulator stage freed by the 4 epilogue warps
+        for (int i = 0; i < kTmStages; ++i)  // accumulator stage freed by the 4 epilogue warps of its group
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(acc_free + 8 * i) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -109,93 +160,109 @@ __global__ void __launch_bounds__(kTmThreads, 1)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
-    const uint32_t slab_bytes = (uint32_t)kblocks * kTmSlab;
+    const uint32_t a_bytes = (uint32_t)a_slabs * kTmSlab, step_bytes = (uint32_t)kStepSlabs * kTmSlab;
 
     if (warp == 0) {
-        // ---------------- TMA producer (one elected lane) ----------------
-        if (lane == 0) {
-            int cur_m = -1, a_loads = 0;
-            int64_t i = 0;
-            for (int64_t t = t_begin; t < t_end; ++t, ++i) {
-                const int mb = (int)(t / n_tiles), nt = (int)(t % n_tiles);
-                if (mb != cur_m) {
-                    if (a_loads > 0) tm_wait(a_free, (uint32_t)((a_loads - 1) & 1));  // MMAs of the previous row block are done
-                    tm_expect_tx(a_full, slab_bytes);
-                    for (int kb = 0; kb < kblocks; ++kb)
-                        tma_load_2d(tm_smem(sA + (size_t)kb * kTmSlab), &map_q, kb * kTmKB, mb * kTmBM, a_full);
-                    cur_m = mb;
-                    ++a_loads;
+        // ---------------- TMA producer: the whole warp walks the loop (converged), lane 0 issues ----------------
+        int cur_m = -1, a_loads = 0;
+        int bs = 0;                 // ring slot of the current step
+        uint32_t lap = 0;           // step / ring_steps
+        for (int64_t h = h_begin; h < h_end;) {
+            const TmTile tile = tm_next_tile(h, h_end, n_half, kTmBN);
+            if (tile.mb != cur_m) {
+                if (a_loads > 0) tm_wait(a_free, (uint32_t)((a_loads - 1) & 1));  // MMAs of the previous row block are done
+                if (lane == 0) {
+                    tm_expect_tx(a_full, a_bytes);
+                    for (int kb = 0; kb < a_slabs; ++kb)  // SPLIT: slab kblocks + kb is the mid half (columns d + kb * 64)
+                        tma_load_2d(tm_smem(sA + (size_t)kb * kTmSlab), &map_q, kb * kTmKB, tile.mb * kTmBM, a_full);
                 }
-                const int st = (int)(i % kTmStages);
-                if (i >= kTmStages) tm_wait(b_free + 8 * st, (uint32_t)(((i / kTmStages) - 1) & 1));
-                tm_expect_tx(b_full + 8 * st, slab_bytes);
-                for (int kb = 0; kb < kblocks; ++kb)
-                    tma_load_2d(tm_smem(sB + ((size_t)st * kblocks + kb) * kTmSlab), &map_mf, kb * kTmKB, nt * kTmBN,
-                                b_full + 8 * st);
+                __syncwarp();
+                cur_m = tile.mb;
+                ++a_loads;
+            }
+            for (int kb = 0; kb < kblocks; ++kb) {
+                if (lap > 0) tm_wait(b_free + 8 * bs, (lap - 1) & 1);
+                if (lane == 0) {
+                    // the box is always the full step (256 rows, or 128 rows x (hi, mid)); rows past S arrive as zeros
+                    tm_expect_tx(b_full + 8 * bs, step_bytes);
+                    uint8_t* dst = sB + (size_t)bs * kStepSlabs * kTmSlab;
+                    tma_load_2d(tm_smem(dst), &map_mf, kb * kTmKB, tile.col0, b_full + 8 * bs);
+                    if constexpr (SPLIT) tma_load_2d(tm_smem(dst + kTmSlab), &map_mf, d + kb * kTmKB, tile.col0, b_full + 8 * bs);
+                }
+                __syncwarp();
+                if (++bs == ring_steps) { bs = 0; ++lap; }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer (one elected lane) ----------------
-        if (lane == 0) {
-            // instruction descriptor: kind::f16, A = B = bf16, D = f32, both K-major, M = 128, N = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTmBN >> 3) << 17) | ((uint32_t)(kTmBM >> 4) << 24);
-            const uint64_t descA0 = tm_desc(tm_smem(sA));
-            int cur_m = -1, a_loads = 0;
-            int64_t i = 0;
-            for (int64_t t = t_begin; t < t_end; ++t, ++i) {
-                const int mb = (int)(t / n_tiles);
-                if (mb != cur_m) {
-                    if (a_loads > 0) tm_commit(a_free);  // every MMA that read the old A block
-                    tm_wait(a_full, (uint32_t)(a_loads & 1));
-                    cur_m = mb;
-                    ++a_loads;
-                }
-                const int st = (int)(i % kTmStages);
-                tm_wait(b_full + 8 * st, (uint32_t)((i / kTmStages) & 1));
-                if (i >= kTmStages) tm_wait(acc_free + 8 * st, (uint32_t)(((i / kTmStages) - 1) & 1));
+        // ---------------- MMA issuer: converged warp, lane 0 issues tcgen05.mma / commit ----------------
+        // instruction descriptor: kind::f16, A = B = bf16, D = f32, both K-major, M = 128, N = tile width
+        const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTmBM >> 4) << 24);
+        const uint64_t descA0 = tm_desc(tm_smem(sA));
+        int cur_m = -1, a_loads = 0;
+        int64_t i = 0;
+        int bs = 0;
+        uint32_t lap = 0;
+        for (int64_t h = h_begin; h < h_end; ++i) {
+            const TmTile tile = tm_next_tile(h, h_end, n_half, kTmBN);
+            const uint32_t idesc = idesc0 | ((uint32_t)(tile.width >> 3) << 17);
+            if (tile.mb != cur_m) {
+                if (a_loads > 0 && lane == 0) tm_commit(a_free);  // every MMA that read the old A block
+                tm_wait(a_full, (uint32_t)(a_loads & 1));
+                cur_m = tile.mb;
+                ++a_loads;
+            }
+            const int st = (int)(i % kTmStages);  // accumulator stage
+            if (i >= kTmStages) tm_wait(acc_free + 8 * st, (uint32_t)(((i / kTmStages) - 1) & 1));
+            const uint32_t tmem_d = tmem_base + (uint32_t)(st * kTmBN);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                tm_wait(b_full + 8 * bs, lap & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint64_t descB0 = tm_desc(tm_smem(sB + (size_t)st * slab_bytes));
-                const uint32_t tmem_d = tmem_base + (uint32_t)(st * kTmBN);
-                for (int kb = 0; kb < kblocks; ++kb) {
+                if (lane == 0) {
+                    const uint64_t a_hi = descA0 + (uint64_t)(((uint32_t)kb * kTmSlab) >> 4);
+                    const uint64_t b_hi = tm_desc(tm_smem(sB + (size_t)bs * kStepSlabs * kTmSlab));
 #pragma unroll
                     for (int ks = 0; ks < kTmKB / 16; ++ks) {
-                        const uint64_t da = descA0 + (uint64_t)(((uint32_t)kb * kTmSlab + ks * 32) >> 4);
-                        const uint64_t db = descB0 + (uint64_t)(((uint32_t)kb * kTmSlab + ks * 32) >> 4);
-                        const uint32_t accumulate = (kb | ks) ? 1u : 0u;
-                        asm volatile(
-                            "{\n\t.reg .pred p;\n\t"
-                            "setp.ne.b32 p, %4, 0;\n\t"
-                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                            :
-                            : "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-                            : "memory");
+                        const uint64_t o = (uint64_t)((ks * 32) >> 4);
+                        if constexpr (SPLIT) {
+                            const uint64_t a_mid = descA0 + (uint64_t)(((uint32_t)(kblocks + kb) * kTmSlab) >> 4);
+                            const uint64_t b_mid = b_hi + (uint64_t)(kTmSlab >> 4);
+                            tm_mma(tmem_d, a_hi + o, b_mid + o, idesc, (kb | ks) ? 1u : 0u);  // small terms first
+                            tm_mma(tmem_d, a_mid + o, b_hi + o, idesc, 1u);
+                            tm_mma(tmem_d, a_hi + o, b_hi + o, idesc, 1u);
+                        } else {
+                            tm_mma(tmem_d, a_hi + o, b_hi + o, idesc, (kb | ks) ? 1u : 0u);
+                        }
                     }
+                    tm_commit(b_free + 8 * bs);  // the ring slot may be overwritten once these MMAs are done
+                    if (kb == kblocks - 1) tm_commit(acc_full + 8 * st);  // the accumulator is complete
                 }
-                tm_commit(b_free + 8 * st);    // the B stage may be overwritten
-                tm_commit(acc_full + 8 * st);  // the accumulator is complete
+                __syncwarp();
+                if (++bs == ring_steps) { bs = 0; ++lap; }
             }
         }
     } else {
-        // ---------------- epilogue: warps 2..5, TMEM lane quarter = warp % 4 ----------------
-        const int quarter = warp & 3;
+        // ---------------- epilogue: group g = warps 2+4g .. 5+4g owns TMEM stage g, lane quarter = warp % 4 ----------------
+        const int quarter = warp & 3, group = (warp - 2) >> 2;
         int cur_m = -1, chunk_no = 0;
         bool row_has_false = false;
         int64_t i = 0;
-        for (int64_t t = t_begin; t < t_end; ++t, ++i) {
-            const int mb = (int)(t / n_tiles), nt = (int)(t % n_tiles);
+        for (int64_t h = h_begin; h < h_end; ++i) {
+            const TmTile tile = tm_next_tile(h, h_end, n_half, kTmBN);
+            if ((int)(i % kTmStages) != group) continue;
+            const int mb = tile.mb;
             const int gm_old = cur_m * kTmBM + quarter * 32 + lane;
             if (mb != cur_m) {
                 if (cur_m >= 0 && attn != nullptr && row_has_false && gm_old < n) atomicOr(row_false + gm_old, 1);
                 cur_m = mb;
                 row_has_false = false;
             }
-            const int st = (int)(i % kTmStages);
+            const int st = group;
             tm_wait(acc_full + 8 * st, (uint32_t)((i / kTmStages) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int gm = mb * kTmBM + quarter * 32 + lane;
-            const int n0 = nt * kTmBN;
+            const int n0 = tile.col0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < kTmBN; c0 += 32) {
+            for (int c0 = 0; c0 < tile.width; c0 += 32) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(st * kTmBN + c0);
                 asm volatile(
@@ -213,18 +280,22 @@ __global__ void __launch_bounds__(kTmThreads, 1)
                     // the warp's 32 x 32 fp32 block goes through shared memory (128-byte rows, 16-byte chunks XOR-swizzled
                     // like the tensor map) and leaves as ONE bulk tensor store of full 128-byte lines; rows >= n and
                     // columns >= S are clipped by the tensor map
-                    uint8_t* buf = sEpi + (size_t)((warp - 2) * 2 + (chunk_no & 1)) * 4096;
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // this buffer's previous store has been read
+                    const uint32_t buf_s = tm_smem(sEpi + (size_t)((warp - 2) * epi_bufs + (epi_bufs > 1 ? (chunk_no & 1) : 0)) * 4096);
+                    if (lane == 0) {  // this buffer's previous store has been read
+                        if (epi_bufs > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     __syncwarp();
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<uint4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                            make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(buf_s + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                                     "r"(v[4 * j]), "r"(v[4 * j + 1]), "r"(v[4 * j + 2]), "r"(v[4 * j + 3])
+                                     : "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&map_out),
-                                     "r"(n0 + c0), "r"(mb * kTmBM + quarter * 32), "r"(tm_smem(buf))
+                                     "r"(n0 + c0), "r"(mb * kTmBM + quarter * 32), "r"(buf_s)
                                      : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
@@ -348,6 +419,27 @@ __global__ void __launch_bounds__(256) layernorm_cast_kernel(const float* __rest
     }
 }
 
+// x[n,d] fp32 -> y[n,2d] bf16 = (hi | mid): hi = bf16(x), mid = bf16(x - hi); x = hi + mid up to 2^-17 relative.
+// One thread per 4 consecutive elements (d % 4 == 0).
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, int64_t quads, int d,
+                                                         __nv_bfloat16* __restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= quads) return;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    const int64_t e = i * 4, row = e / d;
+    const int c = (int)(e - row * d);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 hi[4], mid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        hi[k] = __float2bfloat16_rn(f[k]);
+        mid[k] = __float2bfloat16_rn(f[k] - __bfloat162float(hi[k]));
+    }
+    __nv_bfloat16* yr = y + row * 2 * d + c;
+    *reinterpret_cast<uint2*>(yr) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(yr + d) = *reinterpret_cast<const uint2*>(mid);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -379,13 +471,13 @@ static bool make_out_map(CUtensorMap* map, const void* base, int n, int S) {
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// [rows, d] bf16 row-major -> boxes of 128 rows x 64 elements, 128-byte swizzle, zero fill outside
-static bool make_operand_map(CUtensorMap* map, const void* base, int rows, int d) {
+// [rows, d] bf16 row-major -> boxes of box_rows (128 / 256) rows x 64 elements, 128-byte swizzle, zero fill outside
+static bool make_operand_map(CUtensorMap* map, const void* base, int rows, int d, int box_rows) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (enc == nullptr) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)d * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)kTmKB, (cuuint32_t)kTmBM};
+    const cuuint32_t box[2] = {(cuuint32_t)kTmKB, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -414,32 +506,32 @@ extern "C" int sd3d_layernorm_cast(const float* x, const float* weight, const fl
 
 extern "C" size_t sd3d_mask_logits_bf16_workspace_bytes(int n) { return n > 0 ? (size_t)n * sizeof(int32_t) : 0; }
 
-extern "C" int sd3d_mask_logits_bf16(const void* q_bf16, const void* mf_bf16, int n, int S, int d, float* out, float thr,
-                                     uint8_t* attn_mask, void* ws, size_t ws_bytes, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+// shared launcher of the two operand formats: split = 0 -> [rows, d] bf16, split = 1 -> [rows, 2d] bf16 (hi | mid)
+static int launch_tma(const char* name, const void* q, const void* mf, int n, int S, int d, int split, float* out, float thr,
+                      uint8_t* attn_mask, void* ws, size_t ws_bytes, cudaStream_t stream) {
     if (n < 0 || S < 0 || d <= 0) {
-        set_error("sd3d_mask_logits_bf16: bad shape n=%d S=%d d=%d", n, S, d);
+        set_error("%s: bad shape n=%d S=%d d=%d", name, n, S, d);
         return SD3D_ERR_ARG;
     }
     if (n == 0 || S == 0) return SD3D_OK;
     if (d % kTmKB != 0 || d > 256) {
-        set_error("sd3d_mask_logits_bf16: needs d %% 64 == 0 and d <= 256 (d=%d)", d);
+        set_error("%s: needs d %% 64 == 0 and d <= 256 (d=%d)", name, d);
         return SD3D_ERR_UNSUPPORTED;
     }
-    if (q_bf16 == nullptr || mf_bf16 == nullptr || out == nullptr || !aligned16(q_bf16) || !aligned16(mf_bf16) ||
-        !aligned16(out)) {
-        set_error("sd3d_mask_logits_bf16: null or misaligned buffer");
+    if (q == nullptr || mf == nullptr || out == nullptr || !aligned16(q) || !aligned16(mf) || !aligned16(out)) {
+        set_error("%s: null or misaligned buffer", name);
         return SD3D_ERR_ARG;
     }
     if (attn_mask != nullptr && (ws == nullptr || ws_bytes < sd3d_mask_logits_bf16_workspace_bytes(n))) {
-        set_error("sd3d_mask_logits_bf16: the attention mask needs a workspace of n int32 row flags");
+        set_error("%s: the attention mask needs a workspace of n int32 row flags", name);
         return SD3D_ERR_ARG;
     }
     CUtensorMap map_q, map_mf, map_out;
     const int tma_store = (S % 4 == 0) ? 1 : 0;  // the tensor map needs 16-byte row strides; otherwise plain stores
-    if (!make_operand_map(&map_q, q_bf16, n, d) || !make_operand_map(&map_mf, mf_bf16, S, d) ||
-        !make_out_map(&map_out, tma_store ? out : q_bf16, tma_store ? n : 32, tma_store ? S : 32)) {
-        set_error("sd3d_mask_logits_bf16: cuTensorMapEncodeTiled failed");
+    const int kcols = split ? 2 * d : d;
+    if (!make_operand_map(&map_q, q, n, kcols, kTmBM) || !make_operand_map(&map_mf, mf, S, kcols, tm_bn(split != 0)) ||
+        !make_out_map(&map_out, tma_store ? (const void*)out : q, tma_store ? n : 32, tma_store ? S : 32)) {
+        set_error("%s: cuTensorMapEncodeTiled failed", name);
         return SD3D_ERR_CUDA;
     }
     if (attn_mask != nullptr) {
@@ -447,24 +539,65 @@ extern "C" int sd3d_mask_logits_bf16(const void* q_bf16, const void* mf_bf16, in
         thr = t <= 0.0 ? -INFINITY : (t >= 1.0 ? INFINITY : (float)log(t / (1.0 - t)));
         cudaMemsetAsync(ws, 0, (size_t)n * sizeof(int32_t), stream);
     }
-    const size_t smem = (size_t)(d / kTmKB) * kTmSlab * (1 + kTmStages) + 4 * 2 * 4096 + 1024;
+    // shared memory: resident A block + B ring + epilogue staging. bf16: A <= 64 KB, ring of 3 steps x 32 KB (256 rows of
+    // one K block), staging double-buffered (64 KB); bf16x3: A <= 128 KB, ring of 2 steps x 32 KB ((hi, mid) of 128
+    // rows), staging single-buffered (32 KB)
+    const int kblocks = d / kTmKB;
+    const int ring_steps = split ? 2 : 3, epi_bufs = split ? 1 : 2;
+    const size_t smem = ((size_t)(split ? 2 : 1) * kblocks + (size_t)ring_steps * 2) * kTmSlab + (size_t)8 * epi_bufs * 4096 + 1024;
     static std::atomic<uint64_t> attr_set{0};
     if (first_on_device(&attr_set)) {
-        const cudaError_t e = cudaFuncSetAttribute(mask_logits_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)((256 / kTmKB) * kTmSlab * (1 + kTmStages) + 4 * 2 * 4096 + 1024));
+        const int max_smem = 12 * kTmSlab + 8 * 4096 + 1024;  // bf16x3 at d = 256 (bf16: 9 slabs + 64 KB)
+        cudaError_t e = cudaFuncSetAttribute(mask_logits_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(mask_logits_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
         if (e != cudaSuccess) {
             attr_set.store(0);
-            set_error("sd3d_mask_logits_bf16: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
             return SD3D_ERR_CUDA;
         }
     }
-    const int64_t total = (int64_t)((S + kTmBN - 1) / kTmBN) * ((n + kTmBM - 1) / kTmBM);
+    const int64_t total = (int64_t)((S + 127) / 128) * ((n + kTmBM - 1) / kTmBM);  // 128-column half tiles
     const int ctas = (int)imin64(total, num_sms());
-    const int tiles_per_cta = (int)ceil_div64(total, ctas);
-    const int grid = (int)ceil_div64(total, tiles_per_cta);
-    mask_logits_tma_kernel<<<grid, kTmThreads, smem, stream>>>(map_q, map_mf, map_out, tma_store, n, S, d, tiles_per_cta, out,
-                                                               thr, attn_mask, static_cast<int32_t*>(ws));
+    const int halves_per_cta = (int)ceil_div64(total, ctas);
+    const int grid = (int)ceil_div64(total, halves_per_cta);
+    if (split)
+        mask_logits_tma_kernel<true><<<grid, kTmThreads, smem, stream>>>(map_q, map_mf, map_out, tma_store, n, S, d, halves_per_cta,
+                                                                         ring_steps, epi_bufs, out, thr, attn_mask,
+                                                                         static_cast<int32_t*>(ws));
+    else
+        mask_logits_tma_kernel<false><<<grid, kTmThreads, smem, stream>>>(map_q, map_mf, map_out, tma_store, n, S, d, halves_per_cta,
+                                                                          ring_steps, epi_bufs, out, thr, attn_mask,
+                                                                          static_cast<int32_t*>(ws));
     if (attn_mask != nullptr)
         attn_reset_flagged_kernel<<<(n + 7) / 8, 256, 0, stream>>>(attn_mask, static_cast<const int32_t*>(ws), n, S);
-    return check_launch("sd3d_mask_logits_bf16");
+    return check_launch(name);
+}
+
+extern "C" int sd3d_mask_logits_bf16(const void* q_bf16, const void* mf_bf16, int n, int S, int d, float* out, float thr,
+                                     uint8_t* attn_mask, void* ws, size_t ws_bytes, void* stream_) {
+    return launch_tma("sd3d_mask_logits_bf16", q_bf16, mf_bf16, n, S, d, 0, out, thr, attn_mask, ws, ws_bytes,
+                      (cudaStream_t)stream_);
+}
+
+extern "C" int sd3d_mask_logits_bf16x3(const void* q_split, const void* mf_split, int n, int S, int d, float* out, float thr,
+                                       uint8_t* attn_mask, void* ws, size_t ws_bytes, void* stream_) {
+    return launch_tma("sd3d_mask_logits_bf16x3", q_split, mf_split, n, S, d, 1, out, thr, attn_mask, ws, ws_bytes,
+                      (cudaStream_t)stream_);
+}
+
+extern "C" int sd3d_split_bf16(const float* x, int n, int d, void* y_split, void* stream_) {
+    if (n < 0 || d <= 0 || d % 4 != 0) {
+        set_error("sd3d_split_bf16: bad shape n=%d d=%d (d %% 4 == 0)", n, d);
+        return SD3D_ERR_ARG;
+    }
+    if (n == 0) return SD3D_OK;
+    if (x == nullptr || y_split == nullptr || !aligned16(x) || !aligned16(y_split)) {
+        set_error("sd3d_split_bf16: null or misaligned buffer");
+        return SD3D_ERR_ARG;
+    }
+    const int64_t quads = (int64_t)n * d / 4;
+    split_bf16_kernel<<<(unsigned)ceil_div64(quads, 256), 256, 0, (cudaStream_t)stream_>>>(
+        x, quads, d, static_cast<__nv_bfloat16*>(y_split));
+    return check_launch("sd3d_split_bf16");
 }

@@ -650,27 +650,46 @@ def layernorm_cast(x: torch.Tensor, weight: Optional[torch.Tensor] = None, bias:
     return y32, y16
 
 
-def mask_logits_bf16(q_bf16: torch.Tensor, mf_bf16: torch.Tensor, threshold: Optional[float] = None):
+def split_bf16(x: torch.Tensor) -> torch.Tensor:
+    """x [n,d] float32 -> [n,2d] bfloat16 = (hi | mid), hi = bf16(x), mid = bf16(x - hi): the operand format of
+    ``mask_logits_bf16(..., split=True)`` (``sd3d_split_bf16``)."""
+    _need_cuda("x", x)
+    if x.dim() != 2 or x.dtype != torch.float32 or x.shape[1] % 4 != 0:
+        raise ValueError("x must be float32 [n, d] with d % 4 == 0")
+    x = x.contiguous()
+    n, d = x.shape
+    with torch.cuda.device(x.device):
+        y = torch.empty(n, 2 * d, dtype=torch.bfloat16, device=x.device)
+        check(_lib.load().sd3d_split_bf16(_ptr(x), n, d, _ptr(y), _stream()), "sd3d_split_bf16")
+    return y
+
+
+def mask_logits_bf16(q_bf16: torch.Tensor, mf_bf16: torch.Tensor, threshold: Optional[float] = None, split: bool = False):
     """``einsum('nd,md->nm')`` on bf16 operands through the TMA-fed tcgen05 kernel (``sd3d_mask_logits_bf16``):
-    out [n,S] float32 (+ bool attention mask with ``threshold``). d % 64 == 0, d <= 256."""
+    out [n,S] float32 (+ bool attention mask with ``threshold``). d % 64 == 0, d <= 256. ``split=True``: the operands are
+    ``split_bf16`` pairs [rows, 2d] and the product is hi.hi + hi.mid + mid.hi (``sd3d_mask_logits_bf16x3``, fp32-level
+    accuracy)."""
     _need_cuda("q", q_bf16)
     _need_cuda("mf", mf_bf16)
     if q_bf16.dtype != torch.bfloat16 or mf_bf16.dtype != torch.bfloat16 or q_bf16.dim() != 2 or mf_bf16.dim() != 2 \
-            or q_bf16.shape[1] != mf_bf16.shape[1]:
+            or q_bf16.shape[1] != mf_bf16.shape[1] or (split and q_bf16.shape[1] % 2 != 0):
         raise ValueError("need bfloat16 [n,d] x [S,d]")
     q_bf16, mf_bf16 = q_bf16.contiguous(), mf_bf16.contiguous()
     n, d = q_bf16.shape
+    if split:
+        d //= 2
     s = mf_bf16.shape[0]
     dev = q_bf16.device
     lib = _lib.load()
+    fn, name = (lib.sd3d_mask_logits_bf16x3, "sd3d_mask_logits_bf16x3") if split else \
+        (lib.sd3d_mask_logits_bf16, "sd3d_mask_logits_bf16")
     with torch.cuda.device(dev):
         out = torch.empty(n, s, dtype=torch.float32, device=dev)
         attn = torch.empty(n, s, dtype=torch.uint8, device=dev) if threshold is not None else None
         ws_bytes = int(lib.sd3d_mask_logits_bf16_workspace_bytes(n)) if threshold is not None else 0
         ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev) if threshold is not None else None
-        check(lib.sd3d_mask_logits_bf16(_ptr(q_bf16), _ptr(mf_bf16), n, s, d, _ptr(out),
-                                        float(threshold) if threshold is not None else 0.0, _ptr(attn), _ptr(ws), ws_bytes,
-                                        _stream()), "sd3d_mask_logits_bf16")
+        check(fn(_ptr(q_bf16), _ptr(mf_bf16), n, s, d, _ptr(out), float(threshold) if threshold is not None else 0.0,
+                 _ptr(attn), _ptr(ws), ws_bytes, _stream()), name)
     return (out, attn.view(torch.bool)) if threshold is not None else out
 
 
@@ -682,12 +701,15 @@ def _mask_logits_raw(q: torch.Tensor, mf: torch.Tensor, code: int, threshold: Op
     n, d = q.shape
     s = mf.shape[0]
     dev = q.device
-    if code == _lib.BF16 and d % 64 == 0 and d <= 256 and ((n + 127) // 128) * ((s + 127) // 128) >= _TMA_MIN_TILES:
-        # large problem: cast the operands once (what a fused LayerNorm / x_mask epilogue would hand over), then the
-        # TMA-fed kernel
-        _, q16 = layernorm_cast(q, normalize=False, want_f32=False)
-        _, mf16 = layernorm_cast(mf, normalize=False, want_f32=False)
-        res = mask_logits_bf16(q16, mf16, threshold)
+    if d % 64 == 0 and d <= 256 and ((n + 127) // 128) * ((s + 127) // 128) >= _TMA_MIN_TILES:
+        # large problem: convert the operands once (what a fused LayerNorm / x_mask epilogue would hand over), then the
+        # TMA-fed tensor-core kernel: plain bf16 operands, or (hi | mid) bf16 pairs for the fp32-tolerance path
+        if code == _lib.BF16:
+            _, q16 = layernorm_cast(q, normalize=False, want_f32=False)
+            _, mf16 = layernorm_cast(mf, normalize=False, want_f32=False)
+            res = mask_logits_bf16(q16, mf16, threshold)
+        else:
+            res = mask_logits_bf16(split_bf16(q), split_bf16(mf), threshold, split=True)
         if threshold is None:
             return res, None
         return res[0], res[1].view(torch.uint8)

@@ -918,3 +918,30 @@ def test_mask_logits_bf16_tma_kernel(n, s, d):
     if n * s >= 1_000_000:  # the public entry routes large bf16 problems here (after casting the fp32 operands)
         via = sd.mask_logits(q.to(DEV), mf.to(DEV), precision="bf16", threshold=0.5)
         assert torch.equal(via[0], pred) and torch.equal(via[1], attn)
+
+
+@pytest.mark.parametrize("n,s,d", [(5000, 5000, 256), (300, 700, 256), (129, 1023, 64), (1, 130, 128), (1000, 2053, 192)])
+def test_mask_logits_bf16x3_split_kernel(n, s, d):
+    """fp32-tolerance path on the tensor cores: operands split into (hi | mid) bf16 pairs, out = hi.hi + hi.mid + mid.hi
+    in the fp32 TMEM accumulator. Checked against the float64 product at the path's 1e-5 tolerance (measured: ~2e-6 of
+    |q||mf|), the split itself exactly, the attention mask incl. an all-true row, and the public fp32 routing."""
+    g = torch.Generator().manual_seed(3 * n + s)
+    q = torch.nn.functional.layer_norm(torch.randn(n, d, generator=g), (d,))
+    mf = 0.3 * torch.randn(s, d, generator=g)
+    row = min(5, n - 1)
+    mf = mf - 0.25 * q[row][None, :]
+    q2, mf2 = sd.split_bf16(q.to(DEV)), sd.split_bf16(mf.to(DEV))
+    hi = q.to(torch.bfloat16)
+    assert torch.equal(q2[:, :d].cpu(), hi) and torch.equal(q2[:, d:].cpu(), (q - hi.float()).to(torch.bfloat16))
+    pred, attn = sd.mask_logits_bf16(q2, mf2, threshold=0.5, split=True)
+    exact = mo.mask_logits_f64(q, mf)
+    tol = 1e-5 * float(q.norm(dim=1).max() * mf.norm(dim=1).max())
+    assert float((pred.cpu().double() - exact).abs().max()) <= 0.4 * tol  # well inside the 1e-5 of the path
+    mine = pred.cpu()
+    decided = mine.abs().amin(dim=1) > 1e-6
+    assert torch.equal(attn.cpu()[decided], mo.attn_mask_oracle(mine, 0.5)[decided])
+    assert not attn[row].any() and bool((mine[row] < 0).all())
+    assert torch.equal(sd.mask_logits_bf16(q2, mf2, split=True), pred)
+    if n * s >= 1_000_000:  # the public fp32 entry routes large problems here
+        via = sd.mask_logits(q.to(DEV), mf.to(DEV), precision="fp32", threshold=0.5)
+        assert torch.equal(via[0], pred) and torch.equal(via[1], attn)

@@ -29,11 +29,14 @@ for (n, s, d) in [(200, 500, 256), (500, 500, 256), (5000, 5000, 256)]:
     res = {"shape": [n, s, d], "flop": flop}
     _, q16 = sd.layernorm_cast(q, normalize=False, want_f32=False)
     _, mf16 = sd.layernorm_cast(mf, normalize=False, want_f32=False)
+    q2, mf2 = sd.split_bf16(q), sd.split_bf16(mf)
     for name, fn in (("tma_tcgen05_bf16_operands", lambda: sd.mask_logits_bf16(q16, mf16)),
+                     ("tma_tcgen05_bf16x3_split_operands", lambda: sd.mask_logits_bf16(q2, mf2, split=True)),
+                     ("tma_tcgen05_bf16x3_split_operands+attn_mask", lambda: sd.mask_logits_bf16(q2, mf2, threshold=0.5, split=True)),
                      ("tma_tcgen05_bf16_operands+attn_mask", lambda: sd.mask_logits_bf16(q16, mf16, threshold=0.5)),
                      ("tcgen05_bf16", lambda: sd.mask_logits(q, mf, precision="bf16")),
                      ("tcgen05_bf16+attn_mask", lambda: sd.mask_logits(q, mf, precision="bf16", threshold=0.5)),
-                     ("ffma_fp32", lambda: sd.mask_logits(q, mf, precision="fp32")),
+                     ("fp32_entry(ffma<64 tiles<=bf16x3)", lambda: sd.mask_logits(q, mf, precision="fp32")),
                      ("torch_einsum_fp32", lambda: torch.einsum("nd,md->nm", q, mf)),
                      ("torch_einsum+mask_epilogue", lambda: (lambda pm: ((pm.sigmoid() < 0.5), pm))(torch.einsum("nd,md->nm", q, mf)))):
         t = timeit(fn, 50 if n >= 5000 else 200)
