@@ -88,6 +88,22 @@ def forward_head_masks(norm_queries: Sequence[torch.Tensor], mask_feats: Sequenc
     return pred_masks, (attn_masks if mask_attention_threshold is not None else None)
 
 
+def fused_out_norm(queries: Sequence[torch.Tensor], norm: torch.nn.LayerNorm) -> List[torch.Tensor]:
+    """``self.out_norm(queries[i])`` (instance_seg_3d_decoder.py:558) for every scene of the batch in ONE launch of the
+    mask head's operand producer (``sd3d_layernorm_cast`` over the concatenated query rows; the per-scene results are
+    views of its output). Under autograd, on CPU tensors or for a norm that is not a plain last-dim LayerNorm it is the
+    module itself, scene by scene."""
+    queries = list(queries)
+    plain = isinstance(norm, torch.nn.LayerNorm) and len(norm.normalized_shape) == 1 and norm.elementwise_affine
+    needs_grad = torch.is_grad_enabled() and (any(q.requires_grad for q in queries) or norm.weight.requires_grad)
+    if not plain or needs_grad or not queries or any((not q.is_cuda) or q.dtype != torch.float32 or q.dim() != 2
+                                                     for q in queries) or queries[0].shape[1] > 1024:
+        return [norm(q) for q in queries]
+    rows = torch.cat(queries) if len(queries) > 1 else queries[0]
+    y32, _ = ops.layernorm_cast(rows, norm.weight, norm.bias, norm.eps, normalize=True, want_f32=True, want_bf16=False)
+    return list(y32.split([q.shape[0] for q in queries]))
+
+
 class PointFeatureLifter:
     """Pre-backbone hook: lifts DINO-X maps to per-point features on the GPU and stores them where the
     reference expects the precomputed ones.
@@ -126,7 +142,8 @@ def register_dropins(registry_module=None):
       (spconvunet.py:17, minkunet.py:16) is rebound to :func:`ops.scatter_mean` (CUDA tensors; CPU tensors keep the
       original function, so dataset workers are unaffected);
     * the decoder overrides only ``_forward_head`` (instance_seg_3d_decoder.py:532-577): heads as in the parent, the
-      einsum + attention-mask epilogue of :567-573 through one batched launch (:func:`forward_head_masks`).
+      einsum + attention-mask epilogue of :567-573 through one batched launch (:func:`forward_head_masks`), ``out_norm``
+      (:558) for all scenes in one launch of the operand producer (:func:`fused_out_norm`).
 
     Needs the reference package and its dependencies to be importable (mmengine, spconv, MinkowskiEngine); raises
     ImportError otherwise. Returns the dict of registered classes."""
@@ -164,7 +181,7 @@ def register_dropins(registry_module=None):
         mask_precision = "fp32"  # "bf16": tcgen05 tensor-core kernel (<= 1e-2)
 
         def _forward_head(self, queries, mask_feats, last_flag):
-            norm = [self.out_norm(q) for q in queries]
+            norm = fused_out_norm(queries, self.out_norm)   # one launch for the whole batch (inference)
             cls_preds = [self.out_cls(nq) for nq in norm]
             sem_preds = [self.out_sem(nq) for nq in norm] if last_flag else None
             pred_scores = [self.out_score(nq) if self.objectness_flag else None for nq in norm]

@@ -945,3 +945,24 @@ def test_mask_logits_bf16x3_split_kernel(n, s, d):
     if n * s >= 1_000_000:  # the public fp32 entry routes large problems here
         via = sd.mask_logits(q.to(DEV), mf.to(DEV), precision="fp32", threshold=0.5)
         assert torch.equal(via[0], pred) and torch.equal(via[1], attn)
+
+
+def test_fused_out_norm_matches_module_per_scene():
+    """plugin.fused_out_norm == [self.out_norm(q) for q in queries] (instance_seg_3d_decoder.py:558), one launch for the
+    batch; under autograd it defers to the module."""
+    from segdino3d_b200 import plugin
+    g = torch.Generator().manual_seed(5)
+    norm = torch.nn.LayerNorm(256).to(DEV)
+    with torch.no_grad():
+        norm.weight.copy_(1 + 0.1 * torch.randn(256, generator=g))
+        norm.bias.copy_(0.05 * torch.randn(256, generator=g))
+    qs = [(torch.randn(n, 256, generator=g) * 2 + 0.3).to(DEV) for n in (200, 1, 317)]
+    with torch.no_grad():
+        got = plugin.fused_out_norm(qs, norm)
+        want = [norm(q) for q in qs]
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and float((a - b).abs().max()) <= 3e-6 * float(b.abs().max())
+    q = qs[0].clone().requires_grad_(True)
+    out = plugin.fused_out_norm([q], norm)[0]
+    out.sum().backward()
+    assert q.grad is not None and out.grad_fn is not None
