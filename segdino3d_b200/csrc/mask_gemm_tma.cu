@@ -300,8 +300,39 @@ __global__ void __launch_bounds__(kTmThreads, 1)
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ++chunk_no;
-                }
-                if (gm < n && n0 + c0 < S) {
+                    if (attn != nullptr) {
+                        // mask bytes from the staged block, transposed: 8 lanes cover the 32 columns of one row, so a store
+                        // instruction writes 4 rows x 32 contiguous bytes (whole sectors) instead of 32 rows x 16 bytes
+                        const int sub = lane & 7, grp = lane >> 3;
+                        const int col = n0 + c0 + 4 * sub;
+                        uint32_t valid = 0;  // byte lanes of columns < S
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) valid |= (col + b < S ? 1u : 0u) << (8 * b);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int r = 4 * k + grp;
+                            float4 f;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                         : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w)
+                                         : "r"(buf_s + r * 128 + ((sub ^ (r & 7)) << 4)));
+                            const uint32_t w = (f.x < thr ? 1u : 0u) | (f.y < thr ? 0x100u : 0u) | (f.z < thr ? 0x10000u : 0u) |
+                                               (f.w < thr ? 0x1000000u : 0u);
+                            const int grow = mb * kTmBM + quarter * 32 + r;
+                            if (grow < n && valid != 0) {
+                                uint8_t* dst = attn + (int64_t)grow * S + col;
+                                if (valid == 0x01010101u) {
+                                    *reinterpret_cast<uint32_t*>(dst) = w;  // S % 4 == 0 on this path: 4-byte aligned
+                                } else {
+#pragma unroll
+                                    for (int b = 0; b < 4; ++b)
+                                        if (col + b < S) dst[b] = (uint8_t)((w >> (8 * b)) & 1u);
+                                }
+                            }
+                            const uint32_t bal = __ballot_sync(kFull, ((w ^ 0x01010101u) & valid) != 0);
+                            if ((lane >> 2) == k) row_has_false |= ((bal >> (8 * (lane & 3))) & 0xFFu) != 0;  // lane = row 4k + grp
+                        }
+                    }
+                } else if (!tma_store && gm < n && n0 + c0 < S) {
                     float* orow = out + (int64_t)gm * S + n0 + c0;
                     if (n0 + c0 + 32 <= S && (S & 3) == 0) {
                         if (!tma_store) {
@@ -520,6 +551,10 @@ static int launch_tma(const char* name, const void* q, const void* mf, int n, in
     }
     if (q == nullptr || mf == nullptr || out == nullptr || !aligned16(q) || !aligned16(mf) || !aligned16(out)) {
         set_error("%s: null or misaligned buffer", name);
+        return SD3D_ERR_ARG;
+    }
+    if (attn_mask != nullptr && (reinterpret_cast<uintptr_t>(attn_mask) & 15) != 0) {
+        set_error("%s: attn_mask must be 16-byte aligned", name);
         return SD3D_ERR_ARG;
     }
     if (attn_mask != nullptr && (ws == nullptr || ws_bytes < sd3d_mask_logits_bf16_workspace_bytes(n))) {

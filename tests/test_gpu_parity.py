@@ -966,3 +966,32 @@ def test_fused_out_norm_matches_module_per_scene():
     out = plugin.fused_out_norm([q], norm)[0]
     out.sum().backward()
     assert q.grad is not None and out.grad_fn is not None
+
+
+def test_c_abi_error_codes_mask_head_producers():
+    """The TMA mask GEMM and its operand producers report unsupported widths, missing workspaces and misaligned buffers as
+    codes + messages; empty problems are a no-op."""
+    import ctypes
+    from segdino3d_b200 import _lib
+    lib = _lib.load()
+    null = ctypes.c_void_p(0)
+    P = lambda t, off=0: ctypes.c_void_p(t.data_ptr() + off)
+    q16 = torch.zeros(256, 96, dtype=torch.bfloat16, device=DEV)
+    out = torch.zeros(256, 256, device=DEV)
+    assert lib.sd3d_mask_logits_bf16(P(q16), P(q16), 256, 256, 96, P(out), 0.0, null, null, 0, null) == _lib.ERR_UNSUPPORTED
+    assert b"d % 64" in lib.sd3d_last_error()
+    q16 = torch.zeros(256, 128, dtype=torch.bfloat16, device=DEV)
+    attn = torch.zeros(256, 256, dtype=torch.uint8, device=DEV)
+    assert lib.sd3d_mask_logits_bf16(P(q16), P(q16), 256, 256, 128, P(out), 0.5, P(attn), null, 0, null) == _lib.ERR_ARG
+    assert b"workspace" in lib.sd3d_last_error()
+    assert lib.sd3d_mask_logits_bf16(P(q16, 2), P(q16), 255, 256, 128, P(out), 0.0, null, null, 0, null) == _lib.ERR_ARG
+    assert lib.sd3d_mask_logits_bf16x3(P(q16), P(q16), 256, 256, 512, P(out), 0.0, null, null, 0, null) == _lib.ERR_UNSUPPORTED
+    assert lib.sd3d_mask_logits_bf16(P(q16), P(q16), 0, 256, 128, P(out), 0.0, null, null, 0, null) == _lib.OK
+    x = torch.zeros(8, 2048, device=DEV)
+    assert lib.sd3d_layernorm_cast(P(x), null, null, 8, 2048, 1e-5, 1, P(x), null, null) == _lib.ERR_ARG   # d > 1024
+    assert lib.sd3d_layernorm_cast(P(x), null, null, 8, 512, 1e-5, 1, null, null, null) == _lib.ERR_ARG    # no output
+    assert lib.sd3d_split_bf16(P(x), 8, 6, P(x), null) == _lib.ERR_ARG                                      # d % 4 != 0
+    with pytest.raises(ValueError):
+        sd.mask_logits_bf16(torch.zeros(4, 64, device=DEV), torch.zeros(4, 64, device=DEV))                # not bf16
+    assert sd.mask_logits_bf16(torch.zeros(0, 64, dtype=torch.bfloat16, device=DEV),
+                               torch.zeros(5, 64, dtype=torch.bfloat16, device=DEV)).shape == (0, 5)
