@@ -130,12 +130,14 @@ __global__ void __launch_bounds__(kTmThreads, 1)
     uint8_t* sA = smem;
     uint8_t* sB = smem + (size_t)a_slabs * kTmSlab;       // ring_steps steps
     uint8_t* sEpi = sB + (size_t)ring_steps * kStepSlabs * kTmSlab;  // 8 epilogue warps x epi_bufs x [32 rows][128 B] (swizzled)
-    // a_full, a_free, b_full[ring], b_free[ring], acc_full[2], acc_free[2]
-    __shared__ __align__(8) uint64_t s_bar[2 + 2 * kTmMaxRing + 2 * kTmStages];
+    // a_full[kb], a_free[kb] (one pair per K block of the A block), b_full[ring], b_free[ring], acc_full[2], acc_free[2]
+    constexpr int kMaxKb = 256 / kTmKB;
+    __shared__ __align__(8) uint64_t s_bar[2 * kMaxKb + 2 * kTmMaxRing + 2 * kTmStages];
     __shared__ uint32_t s_tmem;
-    const uint32_t a_full = tm_smem(&s_bar[0]), a_free = tm_smem(&s_bar[1]);
-    const uint32_t b_full = tm_smem(&s_bar[2]), b_free = tm_smem(&s_bar[2 + kTmMaxRing]);
-    const uint32_t acc_full = tm_smem(&s_bar[2 + 2 * kTmMaxRing]), acc_free = tm_smem(&s_bar[2 + 2 * kTmMaxRing + kTmStages]);
+    const uint32_t a_full = tm_smem(&s_bar[0]), a_free = tm_smem(&s_bar[kMaxKb]);
+    const uint32_t b_full = tm_smem(&s_bar[2 * kMaxKb]), b_free = tm_smem(&s_bar[2 * kMaxKb + kTmMaxRing]);
+    const uint32_t acc_full = tm_smem(&s_bar[2 * kMaxKb + 2 * kTmMaxRing]),
+                   acc_free = tm_smem(&s_bar[2 * kMaxKb + 2 * kTmMaxRing + kTmStages]);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_half = (S + 127) / 128, m_blocks = (n + kTmBM - 1) / kTmBM;
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(kTmThreads, 1)
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2 + 2 * kTmMaxRing + kTmStages; ++i)
+        for (int i = 0; i < 2 * kMaxKb + 2 * kTmMaxRing + kTmStages; ++i)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tm_smem(&s_bar[i])) : "memory");
         for (int i = 0; i < kTmStages; ++i)  // accumulator stage freed by the 4 epilogue warps of its group
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 4;" ::"r"(acc_free + 8 * i) : "memory");
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(kTmThreads, 1)
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem;
-    const uint32_t a_bytes = (uint32_t)a_slabs * kTmSlab, step_bytes = (uint32_t)kStepSlabs * kTmSlab;
+    const uint32_t a_kb_bytes = (uint32_t)(SPLIT ? 2 : 1) * kTmSlab, step_bytes = (uint32_t)kStepSlabs * kTmSlab;
 
     if (warp == 0) {
         // ---------------- TMA producer: the whole warp walks the loop (converged), lane 0 issues ----------------
@@ -170,13 +172,19 @@ __global__ void __launch_bounds__(kTmThreads, 1)
         for (int64_t h = h_begin; h < h_end;) {
             const TmTile tile = tm_next_tile(h, h_end, n_half, kTmBN);
             if (tile.mb != cur_m) {
-                if (a_loads > 0) tm_wait(a_free, (uint32_t)((a_loads - 1) & 1));  // MMAs of the previous row block are done
-                if (lane == 0) {
-                    tm_expect_tx(a_full, a_bytes);
-                    for (int kb = 0; kb < a_slabs; ++kb)  // SPLIT: slab kblocks + kb is the mid half (columns d + kb * 64)
-                        tma_load_2d(tm_smem(sA + (size_t)kb * kTmSlab), &map_q, kb * kTmKB, tile.mb * kTmBM, a_full);
+                // the A block is replaced K block by K block: slab kb is refilled as soon as the last tile of the old row
+                // block has consumed it, while that tile's MMAs on the later K blocks are still running
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    if (a_loads > 0) tm_wait(a_free + 8 * kb, (uint32_t)((a_loads - 1) & 1));
+                    if (lane == 0) {
+                        tm_expect_tx(a_full + 8 * kb, a_kb_bytes);
+                        tma_load_2d(tm_smem(sA + (size_t)kb * kTmSlab), &map_q, kb * kTmKB, tile.mb * kTmBM, a_full + 8 * kb);
+                        if constexpr (SPLIT)  // slab kblocks + kb is the mid half (columns d + kb * 64)
+                            tma_load_2d(tm_smem(sA + (size_t)(kblocks + kb) * kTmSlab), &map_q, d + kb * kTmKB, tile.mb * kTmBM,
+                                        a_full + 8 * kb);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
                 cur_m = tile.mb;
                 ++a_loads;
             }
@@ -205,16 +213,18 @@ __global__ void __launch_bounds__(kTmThreads, 1)
         for (int64_t h = h_begin; h < h_end; ++i) {
             const TmTile tile = tm_next_tile(h, h_end, n_half, kTmBN);
             const uint32_t idesc = idesc0 | ((uint32_t)(tile.width >> 3) << 17);
-            if (tile.mb != cur_m) {
-                if (a_loads > 0 && lane == 0) tm_commit(a_free);  // every MMA that read the old A block
-                tm_wait(a_full, (uint32_t)(a_loads & 1));
+            const bool fresh_a = tile.mb != cur_m;  // first tile of a row block: wait for each A slab before its first use
+            if (fresh_a) {
                 cur_m = tile.mb;
                 ++a_loads;
             }
+            // last tile of the row block (and more work follows): hand each A slab back right after its last use
+            const bool release_a = h < h_end && (int)(h / n_half) != tile.mb;
             const int st = (int)(i % kTmStages);  // accumulator stage
             if (i >= kTmStages) tm_wait(acc_free + 8 * st, (uint32_t)(((i / kTmStages) - 1) & 1));
             const uint32_t tmem_d = tmem_base + (uint32_t)(st * kTmBN);
             for (int kb = 0; kb < kblocks; ++kb) {
+                if (fresh_a) tm_wait(a_full + 8 * kb, (uint32_t)((a_loads - 1) & 1));
                 tm_wait(b_full + 8 * bs, lap & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
@@ -234,6 +244,7 @@ __global__ void __launch_bounds__(kTmThreads, 1)
                         }
                     }
                     tm_commit(b_free + 8 * bs);  // the ring slot may be overwritten once these MMAs are done
+                    if (release_a) tm_commit(a_free + 8 * kb);
                     if (kb == kblocks - 1) tm_commit(acc_full + 8 * st);  // the accumulator is complete
                 }
                 __syncwarp();
