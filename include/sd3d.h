@@ -229,8 +229,11 @@ int sd3d_layernorm_cast(const float* x, const float* weight, const float* bias, 
 /* The same contraction on bf16 operands fed by TMA tensor loads (cp.async.bulk.tensor, 128-byte swizzle) into
  *   tcgen05.mma 128 x 128 x 16 tiles, persistent CTAs, warp-specialised (TMA / MMA / epilogue):
  *   q_bf16[n,d], mf_bf16[S,d] row-major bf16 (d % 64 == 0, d <= 256, 16-byte aligned), out[n,S] f32,
- *   attn_mask nullable as in sd3d_mask_logits; ws: sd3d_mask_logits_bf16_workspace_bytes(n) bytes of row flags
- *   (only read when attn_mask != NULL). Logits within 1e-2 of the fp32 einsum (bf16 operands, fp32 accumulate). */
+ *   attn_mask nullable as in sd3d_mask_logits (16-byte aligned); ws: sd3d_mask_logits_bf16_workspace_bytes(n) bytes of
+ *   row flags + progress counters, only used when attn_mask != NULL. CONTRACT: ws must be ZERO-FILLED before the first
+ *   call that uses it; every successful call hands it back zero-filled (the kernel that finishes a row's last tile
+ *   resets the all-true rows of :570-571 in place and clears its flags), so a persistent ws needs no memset per call.
+ *   One ws per concurrently running call. Logits within 1e-2 of the fp32 einsum (bf16 operands, fp32 accumulate). */
 size_t sd3d_mask_logits_bf16_workspace_bytes(int n);
 int sd3d_mask_logits_bf16(const void* q_bf16, const void* mf_bf16, int n, int S, int d, float* out, float thr,
                           uint8_t* attn_mask, void* ws, size_t ws_bytes, void* stream);

@@ -12,7 +12,8 @@
 //              accumulator stages and commits to the mbarriers that free the B ring slot and publish the accumulator;
 //   * warps 2-9 are two epilogue groups, one per TMEM stage (tiles alternate between them): each warp reads its lane
 //              quarter with tcgen05.ld, stages 32 x 32 fp32 blocks in shared memory and stores them with
-//              cp.async.bulk.tensor (full 128-byte lines), writes the thresholded mask bytes and tracks all-true rows.
+//              cp.async.bulk.tensor (full 128-byte lines), writes the thresholded mask bytes, tracks all-true rows and -- the warp that
+//              finishes the last tile of its 32 rows -- resets them in place (flags + progress counters in `ws`).
 // Persistent CTAs (one per SM, 225 KB of shared memory): CTA c owns a contiguous range of 128-column half tiles
 // (row block major), reloading the 128 x d A block only when the row block changes.
 //
@@ -254,19 +255,14 @@ __global__ void __launch_bounds__(kTmThreads, 1)
     } else {
         // ---------------- epilogue: group g = warps 2+4g .. 5+4g owns TMEM stage g, lane quarter = warp % 4 ----------------
         const int quarter = warp & 3, group = (warp - 2) >> 2;
-        int cur_m = -1, chunk_no = 0;
+        int chunk_no = 0;
         bool row_has_false = false;
+        int32_t* progress = row_false + n;  // [m_blocks][4]: half tiles finished per (row block, lane quarter)
         int64_t i = 0;
         for (int64_t h = h_begin; h < h_end; ++i) {
             const TmTile tile = tm_next_tile(h, h_end, n_half, kTmBN);
             if ((int)(i % kTmStages) != group) continue;
             const int mb = tile.mb;
-            const int gm_old = cur_m * kTmBM + quarter * 32 + lane;
-            if (mb != cur_m) {
-                if (cur_m >= 0 && attn != nullptr && row_has_false && gm_old < n) atomicOr(row_false + gm_old, 1);
-                cur_m = mb;
-                row_has_false = false;
-            }
             const int st = group;
             tm_wait(acc_full + 8 * st, (uint32_t)((i / kTmStages) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -393,9 +389,36 @@ __global__ void __launch_bounds__(kTmThreads, 1)
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) tm_arrive(acc_free + 8 * st);
+            if (attn != nullptr) {
+                // publish this warp's 32 rows of the tile: the "row has a false entry" flags, then (behind a fence) the
+                // progress counter of its (row block, quarter). The warp that completes the counter knows every mask byte
+                // of those rows is written and resets the all-true rows (instance_seg_3d_decoder.py:570-571) right here:
+                // no second pass over the mask, no extra launch. Flags and counters are handed back zeroed.
+                if (row_has_false && gm < n) atomicOr(row_false + gm, 1);
+                row_has_false = false;
+                __threadfence();
+                __syncwarp();
+                const int halves = tile.width >> 7;
+                int done = 0;
+                if (lane == 0) done = atomicAdd(progress + mb * 4 + quarter, halves) + halves;
+                done = __shfl_sync(kFull, done, 0);
+                if (done == n_half) {
+                    __threadfence();
+                    const int flag = gm < n ? atomicExch(row_false + gm, 0) : 1;
+                    uint32_t reset = __ballot_sync(kFull, flag == 0);
+                    while (reset) {
+                        const int r = __ffs(reset) - 1;
+                        reset &= reset - 1;
+                        uint8_t* arow = attn + (int64_t)(mb * kTmBM + quarter * 32 + r) * S;
+                        if ((S & 3) == 0)
+                            for (int c = lane; c < (S >> 2); c += 32) reinterpret_cast<uint32_t*>(arow)[c] = 0u;
+                        else
+                            for (int c = lane; c < S; c += 32) arow[c] = 0;
+                    }
+                    if (lane == 0) progress[mb * 4 + quarter] = 0;
+                }
+            }
         }
-        const int gm_last = cur_m * kTmBM + quarter * 32 + lane;
-        if (cur_m >= 0 && attn != nullptr && row_has_false && gm_last < n) atomicOr(row_false + gm_last, 1);
         if (tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory stays valid until read
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -405,14 +428,6 @@ __global__ void __launch_bounds__(kTmThreads, 1)
                      "r"((uint32_t)(kTmBN * kTmStages))
                      : "memory");
     }
-}
-
-// rows with no false entry (all-true) are reset to all-false (instance_seg_3d_decoder.py:570-571); warp per row
-__global__ void attn_reset_flagged_kernel(uint8_t* __restrict__ attn, const int32_t* __restrict__ row_false, int n, int S) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n || row_false[row] != 0) return;
-    uint8_t* r = attn + (int64_t)row * S;
-    for (int c = threadIdx.x & 31; c < S; c += 32) r[c] = 0;
 }
 
 // y = LayerNorm(x) * w + b over the last dimension (w, b nullable: plain copy / cast), written as fp32 and / or bf16.
@@ -546,7 +561,10 @@ extern "C" int sd3d_layernorm_cast(const float* x, const float* weight, const fl
     return check_launch("sd3d_layernorm_cast");
 }
 
-extern "C" size_t sd3d_mask_logits_bf16_workspace_bytes(int n) { return n > 0 ? (size_t)n * sizeof(int32_t) : 0; }
+// n row flags + 4 progress counters per 128-row block
+extern "C" size_t sd3d_mask_logits_bf16_workspace_bytes(int n) {
+    return n > 0 ? ((size_t)n + 4 * (size_t)((n + kTmBM - 1) / kTmBM)) * sizeof(int32_t) : 0;
+}
 
 // shared launcher of the two operand formats: split = 0 -> [rows, d] bf16, split = 1 -> [rows, 2d] bf16 (hi | mid)
 static int launch_tma(const char* name, const void* q, const void* mf, int n, int S, int d, int split, float* out, float thr,
@@ -569,7 +587,7 @@ static int launch_tma(const char* name, const void* q, const void* mf, int n, in
         return SD3D_ERR_ARG;
     }
     if (attn_mask != nullptr && (ws == nullptr || ws_bytes < sd3d_mask_logits_bf16_workspace_bytes(n))) {
-        set_error("%s: the attention mask needs a workspace of n int32 row flags", name);
+        set_error("%s: the attention mask needs a zero-filled workspace of sd3d_mask_logits_bf16_workspace_bytes(n) bytes", name);
         return SD3D_ERR_ARG;
     }
     CUtensorMap map_q, map_mf, map_out;
@@ -583,7 +601,6 @@ static int launch_tma(const char* name, const void* q, const void* mf, int n, in
     if (attn_mask != nullptr) {
         const double t = (double)thr;  // sigmoid(x) < thr  <=>  x < logit(thr)
         thr = t <= 0.0 ? -INFINITY : (t >= 1.0 ? INFINITY : (float)log(t / (1.0 - t)));
-        cudaMemsetAsync(ws, 0, (size_t)n * sizeof(int32_t), stream);
     }
     // shared memory: resident A block + B ring + epilogue staging. bf16: A <= 64 KB, ring of 3 steps x 32 KB (256 rows of
     // one K block), staging double-buffered (64 KB); bf16x3: A <= 128 KB, ring of 2 steps x 32 KB ((hi, mid) of 128
@@ -615,8 +632,6 @@ static int launch_tma(const char* name, const void* q, const void* mf, int n, in
         mask_logits_tma_kernel<false><<<grid, kTmThreads, smem, stream>>>(map_q, map_mf, map_out, tma_store, n, S, d, halves_per_cta,
                                                                           ring_steps, epi_bufs, out, thr, attn_mask,
                                                                           static_cast<int32_t*>(ws));
-    if (attn_mask != nullptr)
-        attn_reset_flagged_kernel<<<(n + 7) / 8, 256, 0, stream>>>(attn_mask, static_cast<const int32_t*>(ws), n, S);
     return check_launch(name);
 }
 

@@ -664,6 +664,9 @@ def split_bf16(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+_MASK_WS: dict = {}   # (device index, stream) -> zero-filled row-flag workspace of the TMA mask kernel
+
+
 def mask_logits_bf16(q_bf16: torch.Tensor, mf_bf16: torch.Tensor, threshold: Optional[float] = None, split: bool = False):
     """``einsum('nd,md->nm')`` on bf16 operands through the TMA-fed tcgen05 kernel (``sd3d_mask_logits_bf16``):
     out [n,S] float32 (+ bool attention mask with ``threshold``). d % 64 == 0, d <= 256. ``split=True``: the operands are
@@ -687,9 +690,19 @@ def mask_logits_bf16(q_bf16: torch.Tensor, mf_bf16: torch.Tensor, threshold: Opt
         out = torch.empty(n, s, dtype=torch.float32, device=dev)
         attn = torch.empty(n, s, dtype=torch.uint8, device=dev) if threshold is not None else None
         ws_bytes = int(lib.sd3d_mask_logits_bf16_workspace_bytes(n)) if threshold is not None else 0
-        ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev) if threshold is not None else None
-        check(fn(_ptr(q_bf16), _ptr(mf_bf16), n, s, d, _ptr(out), float(threshold) if threshold is not None else 0.0,
-                 _ptr(attn), _ptr(ws), ws_bytes, _stream()), name)
+        ws, key = None, None
+        if threshold is not None:
+            # the flag workspace is zero on entry and handed back zeroed by the kernel: keep one per (device, stream)
+            key = (dev.index, _stream())
+            ws = _MASK_WS.get(key)
+            if ws is None or ws.numel() < ws_bytes:
+                ws = _MASK_WS[key] = torch.zeros(max(ws_bytes, 4096), dtype=torch.uint8, device=dev)
+        try:
+            check(fn(_ptr(q_bf16), _ptr(mf_bf16), n, s, d, _ptr(out), float(threshold) if threshold is not None else 0.0,
+                     _ptr(attn), _ptr(ws), ws_bytes, _stream()), name)
+        except Exception:
+            _MASK_WS.pop(key, None)   # its contents are unknown after a failed call
+            raise
     return (out, attn.view(torch.bool)) if threshold is not None else out
 
 
