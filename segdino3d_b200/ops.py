@@ -693,7 +693,7 @@ def mask_logits_bf16(q_bf16: torch.Tensor, mf_bf16: torch.Tensor, threshold: Opt
         ws, key = None, None
         if threshold is not None:
             # the flag workspace is zero on entry and handed back zeroed by the kernel: keep one per (device, stream)
-            key = (dev.index, _stream())
+            key = (dev.index, int(torch.cuda.current_stream().cuda_stream))
             ws = _MASK_WS.get(key)
             if ws is None or ws.numel() < ws_bytes:
                 ws = _MASK_WS[key] = torch.zeros(max(ws_bytes, 4096), dtype=torch.uint8, device=dev)

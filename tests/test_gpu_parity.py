@@ -995,3 +995,22 @@ def test_c_abi_error_codes_mask_head_producers():
         sd.mask_logits_bf16(torch.zeros(4, 64, device=DEV), torch.zeros(4, 64, device=DEV))                # not bf16
     assert sd.mask_logits_bf16(torch.zeros(0, 64, dtype=torch.bfloat16, device=DEV),
                                torch.zeros(5, 64, dtype=torch.bfloat16, device=DEV)).shape == (0, 5)
+
+
+def test_tma_mask_kernel_hands_its_flag_workspace_back_zeroed():
+    """The row flags / progress counters of sd3d_mask_logits_bf16 are self-cleaning (include/sd3d.h contract): after a
+    call the persistent workspace is all zero again and a second call with different data is still right."""
+    from segdino3d_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    for trial in range(2):
+        n, s, d = 1100 + 37 * trial, 1204, 128
+        q = torch.nn.functional.layer_norm(torch.randn(n, d, generator=g), (d,))
+        mf = 0.3 * torch.randn(s, d, generator=g) - 0.3 * q[7 + trial][None, :]   # one all-true row
+        q16, mf16 = q.to(torch.bfloat16).to(DEV), mf.to(torch.bfloat16).to(DEV)
+        pred, attn = sd.mask_logits_bf16(q16, mf16, threshold=0.5)
+        torch.cuda.synchronize()
+        assert all(int(w.count_nonzero()) == 0 for w in ops._MASK_WS.values())
+        mine = pred.cpu()
+        decided = mine.abs().amin(dim=1) > 1e-6
+        assert torch.equal(attn.cpu()[decided], mo.attn_mask_oracle(mine, 0.5)[decided])
+        assert not attn[7 + trial].any() and bool((mine[7 + trial] < 0).all())
