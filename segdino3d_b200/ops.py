@@ -793,6 +793,11 @@ def mask_logits_batched(queries: Sequence[torch.Tensor], mask_feats: Sequence[to
         mfs.append(mf.contiguous())
     dev = qs[0].device
     k = len(qs)
+    if d % 64 == 0 and d <= 256 and any(((q.shape[0] + 127) // 128) * ((mf.shape[0] + 127) // 128) >= _TMA_MIN_TILES
+                                        for q, mf in zip(qs, mfs)):
+        # eval-scale scenes (queries = superpoints): each fills the GPU by itself -> the TMA-fed kernel per scene
+        res = [_mask_logits_raw(q, mf, code, threshold) for q, mf in zip(qs, mfs)]
+        return [r[0] for r in res], ([r[1].view(torch.bool) for r in res] if threshold is not None else None)
     with torch.cuda.device(dev):
         outs = [torch.empty(q.shape[0], mf.shape[0], dtype=torch.float32, device=dev) for q, mf in zip(qs, mfs)]
         attns = [torch.empty(o.shape, dtype=torch.uint8, device=dev) for o in outs] if threshold is not None else None

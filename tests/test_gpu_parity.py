@@ -1014,3 +1014,20 @@ def test_tma_mask_kernel_hands_its_flag_workspace_back_zeroed():
         decided = mine.abs().amin(dim=1) > 1e-6
         assert torch.equal(attn.cpu()[decided], mo.attn_mask_oracle(mine, 0.5)[decided])
         assert not attn[7 + trial].any() and bool((mine[7 + trial] < 0).all())
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
+def test_mask_logits_batched_routes_eval_scale_scenes_to_the_tma_kernel(precision, tol):
+    """A batch with eval-scale scenes (queries = superpoints, >= 64 output tiles) goes scene by scene through the TMA-fed
+    kernel (bf16 / bf16x3); results equal the single-scene entry and the oracle within the precision's tolerance."""
+    g = torch.Generator().manual_seed(21)
+    shapes = [(1500, 1500), (200, 500)]
+    qs = [torch.nn.functional.layer_norm(torch.randn(n, 256, generator=g), (256,)).to(DEV) for n, _ in shapes]
+    mfs = [(0.3 * torch.randn(s, 256, generator=g)).to(DEV) for _, s in shapes]
+    pred, attn = sd.mask_logits_batched(qs, mfs, precision=precision, threshold=0.5)
+    for i in range(2):
+        want = mo.mask_logits_oracle(qs[i].cpu(), mfs[i].cpu())
+        scale = float(qs[i].norm(dim=1).max() * mfs[i].norm(dim=1).max())
+        assert float((pred[i].cpu() - want).abs().max()) <= tol * scale
+        one = sd.mask_logits(qs[i], mfs[i], precision=precision, threshold=0.5)
+        assert torch.equal(one[0], pred[i]) and torch.equal(one[1], attn[i]) and attn[i].dtype == torch.bool
