@@ -422,6 +422,15 @@ def run_ours(args):
         viewshard = sdist.viewshard_report(WORKLOADS[args.viewshard_workload], args.viewshard_workload, "p2p",
                                            args.viewshard_steps, 3, rank, world, dev, args.variant)
 
+    mask_gemm = None
+    if rank == 0 and not args.no_mask:
+        if args.no_viewshard:
+            for b in list(bufs):
+                del bufs[b]
+            del scenes[:]
+            torch.cuda.empty_cache()
+        mask_gemm = mask_gemm_report(dev)
+
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
         traffic, traffic_src = ncu_traffic(args)
@@ -460,11 +469,74 @@ def run_ours(args):
             line["e2e"] = e2e
         if viewshard is not None:
             line["viewshard"] = viewshard
+        if mask_gemm is not None:
+            line["mask_gemm"] = mask_gemm
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(build_scene(wl, 1235))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def mask_gemm_report(dev):
+    """The tensor-core leg of the path (a-5, instance_seg_3d_decoder.py:567-573), timed with CUDA events on rank 0:
+    the eval-scale contraction (queries = superpoints, 5000 x 5000 x 256) through the TMA-fed tcgen05 kernel with
+    bf16 and bf16x3 (fp32-tolerance) operands, and the ScanNet200 decoder shape of BASELINE configs[1] (200 queries x
+    500 superpoints, 8 scenes in one batched launch with the attention mask). Fractions are of the measured dense
+    bf16 peak (MEASURED_PEAKS.json: cuBLAS burst); algorithmic flops = 2 n S d (bf16x3 issues 3x that)."""
+    import torch
+    import segdino3d_b200 as sd
+    from segdino3d_b200.synth import make_decoder_operands
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, peak_src = float(json.load(f)["bf16_tflops"]), "measured (MEASURED_PEAKS.json, burst)"
+    except Exception:
+        peak, peak_src = 2250.0, "nominal dense bf16 (B200_PROFILING.md)"
+
+    def timeit(fn, iters):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters * 1e-3
+
+    n = s = 5000
+    d = 256
+    q, mf = make_decoder_operands(n, s, d)
+    q, mf = q.to(dev), mf.to(dev)
+    _, q16 = sd.layernorm_cast(q, normalize=False, want_f32=False)
+    _, mf16 = sd.layernorm_cast(mf, normalize=False, want_f32=False)
+    q2, mf2 = sd.split_bf16(q), sd.split_bf16(mf)
+    flop = 2.0 * n * s * d
+    t16 = timeit(lambda: sd.mask_logits_bf16(q16, mf16), 50)
+    t16m = timeit(lambda: sd.mask_logits_bf16(q16, mf16, threshold=0.5), 50)
+    tx3 = timeit(lambda: sd.mask_logits_bf16(q2, mf2, split=True), 50)
+    tref = timeit(lambda: torch.einsum("nd,md->nm", q, mf), 20)
+    ops_ = [make_decoder_operands(200, 500, d, seed=i) for i in range(8)]
+    qs, mfs = [o[0].to(dev) for o in ops_], [o[1].to(dev) for o in ops_]
+    tb = timeit(lambda: sd.mask_logits_batched(qs, mfs, precision="bf16", threshold=0.5), 100)
+
+    def torch_head():
+        for a_, b_ in zip(qs, mfs):
+            pm = torch.einsum("nd,md->nm", a_, b_)
+            am = pm.sigmoid() < 0.5
+            am[torch.where(am.sum(-1) == am.shape[-1])] = False
+    tt = timeit(torch_head, 50)
+    return {"bound": "tensor", "kernel": "mask_logits_tma_kernel (TMA loads, tcgen05.mma M128 N256 K16, TMEM, TMA stores)",
+            "shape": [n, s, d], "dtype": "bf16 operands, fp32 accumulate / output", "us": t16 * 1e6,
+            "achieved": flop / t16 / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flop / t16 / 1e12 / peak,
+            "peak_source": peak_src, "us_with_attn_mask": t16m * 1e6,
+            "bf16x3_fp32_tolerance": {"us": tx3 * 1e6, "algorithmic_tflops": flop / tx3 / 1e12,
+                                      "issued_tflops": 3 * flop / tx3 / 1e12},
+            "torch_einsum_fp32_us": tref * 1e6,
+            "decoder_shape_8_scenes": {"shape": [200, 500, d], "batched_bf16_with_attn_mask_us": tb * 1e6,
+                                       "torch_reference_sequence_us": tt * 1e6},
+            "note": "output 100 MB fp32 per call (a fill_ of it alone: ~16.6 us); timings include the host side of each call"}
 
 
 def ncu_traffic(args):
@@ -514,6 +586,7 @@ def main():
     ap.add_argument("--viewshard-workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--viewshard-steps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-mask", action="store_true", help="skip the mask-GEMM (tensor roofline) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
