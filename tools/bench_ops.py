@@ -28,14 +28,32 @@ def torch_scatter_mean(src, idx, s):  # torch_scatter 2.1.2 composite on CUDA (g
     cnt[cnt < 1] = 1
     return out.true_divide_(cnt[:, None])
 
+from segdino3d_b200 import _lib as _l
+from segdino3d_b200.ops import _ptr as _p, _stream as _st
+from segdino3d_b200.synth import make_scene
 g = torch.Generator().manual_seed(0)
-for n, s, c in [(100_000, 500, 256), (100_000, 500, 96), (100_000, 500, 32), (100_000, 500, 3), (1_000_000, 5000, 256)]:
+scene_ids = make_scene(n_points=100_000, n_views=1, hd=24, wd=32, stride=8, channels=4, seed=3).sp_ids  # ScanNet-like sizes
+for n, s, c, ids in [(100_000, 500, 256, "uniform"), (100_000, 500, 96, "uniform"), (100_000, 500, 32, "uniform"),
+                     (100_000, 500, 3, "uniform"), (100_000, 0, 256, "scene"), (100_000, 0, 32, "scene"),
+                     (100_000, 0, 3, "scene"), (1_000_000, 5000, 256, "uniform")]:
     R = 6 if n * c * 4 < 64e6 else 3   # rotate inputs so that they are not L2 resident
     srcs = [torch.randn(n, c, generator=g).to(dev) for _ in range(R)]
-    idx = torch.randint(0, s, (n,), generator=g).to(dev)
+    if ids == "scene":   # superpoint sizes of a synthetic room (a few large planes, many small segments)
+        idx = scene_ids.to(dev)
+        s = int(idx.max()) + 1
+    else:
+        idx = torch.randint(0, s, (n,), generator=g).to(dev)
     plan = sd.sp_sort(idx, s)
     bytes_alg = n * c * 4 + n * 4 + s * c * 4
-    res = {"op": "scatter_mean", "shape": [n, c, s], "algorithmic_bytes": bytes_alg}
+    sizes = torch.bincount(idx.cpu(), minlength=s)
+    res = {"op": "scatter_mean", "shape": [n, c, s], "ids": ids, "largest_superpoint": int(sizes.max()), "algorithmic_bytes": bytes_alg}
+    out_ = torch.empty(s, c, device=dev)
+    lib_ = _l.load()
+    def abi_exact(i):   # the C-ABI call alone into a caller-owned buffer: device time without the python / allocator side
+        lib_.sd3d_sp_mean(_p(srcs[i % R]), _p(plan.perm), _p(plan.seg_offsets), n, s, c, None, _l.POOL_EXACT, None, None, 0, 0,
+                          None, 0, _p(out_), _st())
+    t = timeit(abi_exact, 200)
+    res["sd3d_exact(abi only)"] = {"us": round(t * 1e6, 1), "GBps": round(bytes_alg / t / 1e9, 1), "frac_hbm": round(bytes_alg / t / 1e9 / PEAK, 3)}
     for name, fn in (("sd3d_exact(sort+mean)", lambda i: sd.scatter_mean(srcs[i % R], idx, dim=0, dim_size=s)),
                      ("sd3d_fast(sort+mean)", lambda i: sd.scatter_mean(srcs[i % R], idx, dim=0, dim_size=s, exact=False)),
                      ("sd3d_exact(mean only)", lambda i: sd.sp_mean(srcs[i % R], plan, exact=True)),
