@@ -11,6 +11,9 @@
 //   FAST : superpoints are split into runs of `run` rows (sp_tasks); partial rows are combined in run
 //          order by sp_combine_rows_kernel -> deterministic, <= 1e-5 relative to the oracle.
 // HBM-bound: algorithmic bytes = N*C*4 (src) + N*4 (perm) + S*C*4 (out).
+// Three EXACT kernels, same summation order: sp_mean_cta_kernel (one CTA per superpoint, cp.async ring: sizeable
+// superpoints, narrow rows or few superpoints), sp_mean_small_kernel (several narrow rows per warp load), and the
+// warp-per-(superpoint, slab) kernel below (wide rows, thousands of superpoints: at the HBM copy peak).
 #include <atomic>
 
 #include "common.cuh"
