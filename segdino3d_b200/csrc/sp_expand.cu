@@ -7,8 +7,9 @@
 //         mask_pred = mask_pred_sigmoid > self.test_cfg.sp_score_thr
 //         mask_pointnum = mask_pred.sum(1)
 //     with ONE pass that never materialises the fp32 [K,N] tensor: the comparison is done per superpoint, the
-//     boolean row is expanded with 128-bit stores, the per-instance point count is accumulated with integer
-//     atomics (exact). Write-bound: K*N bytes out, N*8 bytes of ids in (once per 32 rows).
+//     boolean row is expanded with 64-bit stores from a bit-matrix transpose + byte look-up table, the per-instance
+//     point count is accumulated with integer atomics (exact). Write-bound: K*N bytes out, N*8 bytes of ids in (once
+//     per 32 rows).
 // (2) sd3d_sp_mean_backward: grad_src[p,:] = grad_out[idx[p],:] / max(|idx[p]|,1), the gradient of
 //     scatter_mean(src, idx, dim=0) (spconvunet.py:390 is called under autograd in training,
 //     engine/train_engine_3d.py:99-105). Read N*8 + S*C*4 (L2 resident), write N*C*4.
@@ -17,15 +18,39 @@
 namespace sd3d {
 
 constexpr int kExpThreads = 256;
-constexpr int kExpPtsPerThread = 16;  // one 128-bit store of mask bytes
+constexpr int kExpPtsPerThread = 8;   // one 64-bit store of mask bytes per row
 constexpr int kExpRows = 32;          // instances per CTA: the ids are loaded once for 32 output rows
+constexpr int kExpMaxChunks = 31;     // chunks per CTA: the per-thread row counters are bytes (8 points per chunk)
 
-__global__ void __launch_bounds__(kExpThreads)
+// 8 x 8 bit-matrix transpose of a 64-bit word (byte j = row j): byte r of the result holds bit r of every input byte
+__device__ __forceinline__ uint64_t transpose8x8(uint64_t x) {
+    uint64_t t;
+    t = (x ^ (x >> 7)) & 0x00AA00AA00AA00AAull;
+    x = x ^ t ^ (t << 7);
+    t = (x ^ (x >> 14)) & 0x0000CCCC0000CCCCull;
+    x = x ^ t ^ (t << 14);
+    t = (x ^ (x >> 28)) & 0x00000000F0F0F0F0ull;
+    x = x ^ t ^ (t << 28);
+    return x;
+}
+// per-byte population count of a 64-bit word
+__device__ __forceinline__ uint64_t popcount_bytes(uint64_t x) {
+    x = x - ((x >> 1) & 0x5555555555555555ull);
+    x = (x & 0x3333333333333333ull) + ((x >> 2) & 0x3333333333333333ull);
+    return (x + (x >> 4)) & 0x0F0F0F0F0F0F0F0Full;
+}
+
+__global__ void __launch_bounds__(kExpThreads, 4)
     sp_expand_mask_kernel(const float* __restrict__ mask_sig, const int64_t* __restrict__ superpoints, int K, int S,
-                          int64_t N, float thr, uint8_t* __restrict__ out, int32_t* __restrict__ pointnum) {
-    // s_word[s] bit r = (mask_sig[k0+r, s] > thr): ONE shared-memory lookup per point yields the bits of all
-    // 32 instance rows this CTA writes
+                          int64_t N, float thr, uint8_t* __restrict__ out, int32_t* __restrict__ pointnum, int vec_io) {
+    // s_word[s] bit r = (mask_sig[k0+r, s] > thr): ONE shared-memory lookup per point yields the bits of all 32 instance
+    // rows this CTA writes. A thread owns 8 consecutive points: their 8 words are an 8 x 32 bit matrix whose transpose
+    // (four 8 x 8 blocks, 64-bit SWAR) gives, per row, the 8 points' bits as ONE byte; s_lut turns that byte into the 8
+    // output bytes (one LDS.64 + one 64-bit store per row instead of 8 extract / shift / or steps), and a per-byte
+    // population count of the transposed blocks feeds the per-instance point counts (bytes in registers, reduced once
+    // per CTA).
     extern __shared__ uint32_t s_word[];
+    __shared__ uint2 s_lut[256];
     __shared__ int32_t s_cnt[kExpRows];
     const int k0 = blockIdx.y * kExpRows;
     const int rows = min(kExpRows, K - k0);
@@ -34,39 +59,68 @@ __global__ void __launch_bounds__(kExpThreads)
         for (int r = 0; r < rows; ++r) w |= (__ldg(mask_sig + (int64_t)(k0 + r) * S + s) > thr ? 1u : 0u) << r;
         s_word[s] = w;
     }
+    {
+        const uint32_t t = threadIdx.x;  // kExpThreads == 256: byte value -> its 8 bits as bytes
+        s_lut[t] = make_uint2(((t & 15u) * 0x00204081u) & 0x01010101u, ((t >> 4) * 0x00204081u) & 0x01010101u);
+    }
     if (threadIdx.x < kExpRows) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const int64_t n_chunks = ceil_div64(N, (int64_t)kExpThreads * kExpPtsPerThread);
-    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {  // the word table is built once per CTA
-    const int64_t p0 = (chunk * kExpThreads + threadIdx.x) * kExpPtsPerThread;
-    uint32_t pw[kExpPtsPerThread];
+    uint64_t cnt[4] = {0ull, 0ull, 0ull, 0ull};  // byte i of cnt[k]: this thread's points in row 8k + i (<= 8 per chunk)
+    const bool n_vec = vec_io && (N & 7) == 0;  // 64-bit stores: rows and the base pointer are 8-byte aligned
+    for (int64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {  // the tables are built once per CTA
+        const int64_t p0 = (chunk * kExpThreads + threadIdx.x) * kExpPtsPerThread;
+        uint32_t pw[kExpPtsPerThread];
+        if (vec_io && p0 + kExpPtsPerThread <= N) {
+            const longlong2* ids = reinterpret_cast<const longlong2*>(superpoints + p0);  // 16-byte aligned: p0 % 8 == 0
 #pragma unroll
-    for (int j = 0; j < kExpPtsPerThread; ++j) {
-        const int64_t p = p0 + j;
-        const int64_t id = p < N ? __ldg(superpoints + p) : -1;
-        pw[j] = (id >= 0 && id < S) ? s_word[id] : 0u;  // ids outside [0,S) expand to False
-    }
-    const bool vec_ok = (p0 + kExpPtsPerThread <= N) && ((N & 15) == 0);
-    for (int r = 0; r < rows; ++r) {
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < kExpPtsPerThread; ++j) {
-            const uint32_t b = (pw[j] >> r) & 1u;
-            w[j >> 2] |= b << (8 * (j & 3));
-            c += (int)b;
-        }
-        uint8_t* dst = out + (int64_t)(k0 + r) * N + p0;
-        if (vec_ok) {
-            __stcs(reinterpret_cast<uint4*>(dst), make_uint4(w[0], w[1], w[2], w[3]));
+            for (int j = 0; j < kExpPtsPerThread / 2; ++j) {
+                const longlong2 id = __ldg(ids + j);
+                pw[2 * j] = (id.x >= 0 && id.x < S) ? s_word[id.x] : 0u;  // ids outside [0,S) expand to False
+                pw[2 * j + 1] = (id.y >= 0 && id.y < S) ? s_word[id.y] : 0u;
+            }
         } else {
 #pragma unroll
-            for (int j = 0; j < kExpPtsPerThread; ++j)
-                if (p0 + j < N) dst[j] = (uint8_t)((w[j >> 2] >> (8 * (j & 3))) & 1u);
+            for (int j = 0; j < kExpPtsPerThread; ++j) {
+                const int64_t pt = p0 + j;
+                const int64_t id = pt < N ? __ldg(superpoints + pt) : -1;
+                pw[j] = (id >= 0 && id < S) ? s_word[id] : 0u;
+            }
         }
-        c = __reduce_add_sync(kFull, c);  // one REDUX per row, one smem atomic per warp
-        if (lane_id() == 0 && c) atomicAdd(&s_cnt[r], c);
+        const bool vec_ok = n_vec && (p0 + kExpPtsPerThread <= N);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // rows 8k .. 8k+7
+            // byte k of the 8 words, point j in byte j
+            const uint32_t lo = __byte_perm(__byte_perm(pw[0], pw[1], 0x0040 + 0x11 * k), __byte_perm(pw[2], pw[3], 0x0040 + 0x11 * k), 0x5410);
+            const uint32_t hi = __byte_perm(__byte_perm(pw[4], pw[5], 0x0040 + 0x11 * k), __byte_perm(pw[6], pw[7], 0x0040 + 0x11 * k), 0x5410);
+            const uint64_t t = transpose8x8(((uint64_t)hi << 32) | lo);  // byte i: bit j = point j of row 8k + i
+            cnt[k] += popcount_bytes(t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 8 * k + i;
+                if (r < rows) {
+                    const uint2 bytes = s_lut[(uint32_t)(t >> (8 * i)) & 0xFFu];
+                    uint8_t* dst = out + (int64_t)(k0 + r) * N + p0;
+                    if (vec_ok) {
+                        __stcs(reinterpret_cast<uint2*>(dst), bytes);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < kExpPtsPerThread; ++j)
+                            if (p0 + j < N) dst[j] = (uint8_t)(((j < 4 ? bytes.x : bytes.y) >> (8 * (j & 3))) & 1u);
+                    }
+                }
+            }
+        }
     }
+    // per-instance point counts: bytes -> one REDUX per row per warp, one shared atomic per warp, one global per CTA
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int c = (int)((cnt[k] >> (8 * i)) & 0xFFull);
+            c = __reduce_add_sync(kFull, c);
+            if (lane_id() == 0 && c) atomicAdd(&s_cnt[8 * k + i], c);
+        }
     }
     __syncthreads();
     if (threadIdx.x < rows && s_cnt[threadIdx.x]) atomicAdd(pointnum + k0 + threadIdx.x, s_cnt[threadIdx.x]);
@@ -143,10 +197,12 @@ extern "C" int sd3d_sp_expand_mask(const float* mask_sig, const int64_t* superpo
     }
     const int64_t n_chunks = ceil_div64(N, (int64_t)kExpThreads * kExpPtsPerThread);
     const int row_groups = (K + kExpRows - 1) / kExpRows;
-    // ~4 CTAs per SM in total: every CTA builds its 32-row word table once and then loops over point chunks
-    const int64_t gx = imin64(n_chunks, imax64(1, (int64_t)4 * num_sms() / row_groups));
+    // ~4 CTAs per SM in total: every CTA builds its 32-row word table once and then loops over point chunks (at most
+    // kExpMaxChunks of them: the per-thread row counters are bytes)
+    const int64_t gx = imin64(n_chunks, imax64(imax64(1, (int64_t)4 * num_sms() / row_groups), ceil_div64(n_chunks, kExpMaxChunks)));
     dim3 grid((unsigned)gx, (unsigned)row_groups);
-    sp_expand_mask_kernel<<<grid, kExpThreads, smem, stream>>>(mask_sig, superpoints, K, (int)S, N, thr, out, pointnum);
+    const int vec_io = aligned16(superpoints) && (reinterpret_cast<uintptr_t>(out) & 7) == 0;
+    sp_expand_mask_kernel<<<grid, kExpThreads, smem, stream>>>(mask_sig, superpoints, K, (int)S, N, thr, out, pointnum, vec_io);
     return check_launch("sd3d_sp_expand_mask");
 }
 

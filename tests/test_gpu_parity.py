@@ -1031,3 +1031,20 @@ def test_mask_logits_batched_routes_eval_scale_scenes_to_the_tma_kernel(precisio
         assert float((pred[i].cpu() - want).abs().max()) <= tol * scale
         one = sd.mask_logits(qs[i], mfs[i], precision=precision, threshold=0.5)
         assert torch.equal(one[0], pred[i]) and torch.equal(one[1], attn[i]) and attn[i].dtype == torch.bool
+
+
+def test_expand_superpoint_masks_edges():
+    """Ids outside [0, S) expand to False, a superpoint-id view that is not 16-byte aligned takes the scalar id loads, a
+    point count that is not a multiple of 8 takes the byte stores, and a large N exercises several chunks per CTA."""
+    g = torch.Generator().manual_seed(9)
+    k, s, n = 70, 211, 300_007
+    m = torch.rand(k, s, generator=g)
+    sp = torch.randint(-2, s + 3, (n + 1,), generator=g)
+    want_full = torch.zeros(k, n + 1, dtype=torch.bool)
+    ok = (sp >= 0) & (sp < s)
+    want_full[:, ok] = m[:, sp[ok]] > 0.6
+    sp_dev = sp.to(DEV)
+    got, cnt = sd.expand_superpoint_masks(m.to(DEV), sp_dev[1:], 0.6)          # misaligned view, n odd
+    assert torch.equal(got.cpu(), want_full[:, 1:]) and torch.equal(cnt.cpu(), want_full[:, 1:].sum(1))
+    got, cnt = sd.expand_superpoint_masks(m.to(DEV), sp_dev[:300_000].contiguous(), 0.6)   # aligned, n % 8 == 0
+    assert torch.equal(got.cpu(), want_full[:, :300_000]) and torch.equal(cnt.cpu(), want_full[:, :300_000].sum(1))
