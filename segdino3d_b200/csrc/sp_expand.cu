@@ -54,10 +54,26 @@ __global__ void __launch_bounds__(kExpThreads, 4)
     __shared__ int32_t s_cnt[kExpRows];
     const int k0 = blockIdx.y * kExpRows;
     const int rows = min(kExpRows, K - k0);
-    for (int s = threadIdx.x; s < S; s += kExpThreads) {
-        uint32_t w = 0u;
-        for (int r = 0; r < rows; ++r) w |= (__ldg(mask_sig + (int64_t)(k0 + r) * S + s) > thr ? 1u : 0u) << r;
-        s_word[s] = w;
+    if (rows == kExpRows) {  // full row group: 16 independent loads in flight per thread (the table build is latency-bound)
+        for (int s = threadIdx.x; s < S; s += kExpThreads) {
+            const float* col = mask_sig + (int64_t)k0 * S + s;
+            uint32_t w = 0u;
+#pragma unroll
+            for (int r0 = 0; r0 < kExpRows; r0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) v[r] = __ldg(col + (int64_t)(r0 + r) * S);
+#pragma unroll
+                for (int r = 0; r < 16; ++r) w |= (v[r] > thr ? 1u : 0u) << (r0 + r);
+            }
+            s_word[s] = w;
+        }
+    } else {
+        for (int s = threadIdx.x; s < S; s += kExpThreads) {
+            uint32_t w = 0u;
+            for (int r = 0; r < rows; ++r) w |= (__ldg(mask_sig + (int64_t)(k0 + r) * S + s) > thr ? 1u : 0u) << r;
+            s_word[s] = w;
+        }
     }
     {
         const uint32_t t = threadIdx.x;  // kExpThreads == 256: byte value -> its 8 bits as bytes
