@@ -475,6 +475,7 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_baseline(build_scene(wl, 1235))
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()  # rank 0 measures the mask GEMM and prints while the others wait here
         dist.destroy_process_group()
 
 
