@@ -126,3 +126,32 @@ def test_bench_reads_ncu_traffic_from_profiles():
     traffic, src = bench.ncu_traffic(argparse.Namespace(workload="cfg2", variant=0, run=32))
     assert src.startswith("profiles/") and 250e6 < traffic < 500e6
     assert bench.ncu_traffic(argparse.Namespace(workload="cfg4", variant=0, run=32))[0] is None
+
+
+def test_mask_head_entries_validate_on_the_host():
+    """The TMA mask GEMM and its operand producers reject bad shapes before touching the device, report the documented
+    workspace size, and the python mirror has no CPU fallback for them."""
+    lib = _lib.load()
+    assert lib.sd3d_mask_logits_bf16_workspace_bytes(0) == 0
+    assert lib.sd3d_mask_logits_bf16_workspace_bytes(300) == (300 + 4 * 3) * 4      # row flags + 4 counters per 128 rows
+    assert lib.sd3d_mask_logits_bf16(None, None, 8, 8, 100, None, 0.0, None, None, 0, None) == _lib.ERR_UNSUPPORTED   # d % 64
+    assert lib.sd3d_mask_logits_bf16(None, None, 8, 8, 128, None, 0.0, None, None, 0, None) == _lib.ERR_ARG           # null
+    assert lib.sd3d_mask_logits_bf16x3(None, None, -1, 8, 128, None, 0.0, None, None, 0, None) == _lib.ERR_ARG
+    assert lib.sd3d_mask_logits_bf16x3(None, None, 0, 8, 128, None, 0.0, None, None, 0, None) == _lib.OK              # empty
+    assert lib.sd3d_layernorm_cast(None, None, None, 4, 4096, 1e-5, 1, None, None, None) == _lib.ERR_ARG
+    assert lib.sd3d_split_bf16(None, 4, 6, None, None) == _lib.ERR_ARG
+    assert lib.sd3d_split_bf16(None, 0, 8, None, None) == _lib.OK
+    for fn, args in ((sd.layernorm_cast, (torch.zeros(2, 8),)), (sd.split_bf16, (torch.zeros(2, 8),)),
+                     (sd.mask_logits_bf16, (torch.zeros(2, 64, dtype=torch.bfloat16), torch.zeros(3, 64, dtype=torch.bfloat16)))):
+        with pytest.raises(sd.Sd3dError):
+            fn(*args)
+
+
+def test_fused_out_norm_defers_to_the_module_off_the_gpu():
+    """plugin.fused_out_norm is the module itself for CPU tensors / autograd / non-plain norms (no silent kernel path)."""
+    from segdino3d_b200 import plugin
+    norm = torch.nn.LayerNorm(16)
+    qs = [torch.randn(5, 16), torch.randn(3, 16)]
+    got = plugin.fused_out_norm(qs, norm)
+    assert all(torch.equal(a, norm(q)) for a, q in zip(got, qs))
+    assert plugin.fused_out_norm([], norm) == []
