@@ -246,6 +246,16 @@ int sd3d_mask_logits_bf16(const void* q_bf16, const void* mf_bf16, int n, int S,
  *   q_split[n,2d], mf_split[S,2d]. Replaces the FFMA path of sd3d_mask_logits for large problems
  *   (instance_seg_3d_decoder.py:567 at eval scale: the reference runs this einsum in fp32, amp=False). */
 int sd3d_split_bf16(const float* x, int n, int d, void* y_split, void* stream);
+
+/* fp32 operands in, ONE host call: converts q / mf (plain bf16 cast for precision == SD3D_BF16, the (hi | mid) split for
+ *   SD3D_F32 = fp32 tolerance) into `scratch` (sd3d_mask_logits_large_scratch_bytes(); contents irrelevant) and runs the
+ *   TMA-fed kernel; `flags` is the zero-filled self-cleaning workspace of sd3d_mask_logits_bf16 (used with attn_mask
+ *   only). The einsum + epilogue of instance_seg_3d_decoder.py:567-573 at eval scale; what ops.mask_logits calls for
+ *   problems of >= 64 output tiles. */
+size_t sd3d_mask_logits_large_scratch_bytes(int n, int S, int d, int precision);
+int sd3d_mask_logits_large(const float* q, const float* mf, int n, int S, int d, int precision, float* out, float thr,
+                           uint8_t* attn_mask, void* scratch, size_t scratch_bytes, void* flags, size_t flags_bytes,
+                           void* stream);
 int sd3d_mask_logits_bf16x3(const void* q_split, const void* mf_split, int n, int S, int d, float* out, float thr,
                             uint8_t* attn_mask, void* ws, size_t ws_bytes, void* stream);
 

@@ -68,6 +68,9 @@ SYMBOLS = {
     "sd3d_mask_logits_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p,
                                       c_size_t, c_void_p]),
     "sd3d_split_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "sd3d_mask_logits_large_scratch_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "sd3d_mask_logits_large": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p,
+                                       c_size_t, c_void_p, c_size_t, c_void_p]),
     "sd3d_mask_logits_bf16x3": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_void_p,
                                         c_size_t, c_void_p]),
     "sd3d_mask_logits_batched": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_float,

@@ -497,6 +497,15 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
     *reinterpret_cast<uint2*>(yr + d) = *reinterpret_cast<const uint2*>(mid);
 }
 
+// x[n*d] fp32 -> bf16, 4 elements per thread (the plain operand cast: no normalisation, no affine)
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ x, int64_t quads, __nv_bfloat16* __restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= quads) return;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    __nv_bfloat16 h[4] = {__float2bfloat16_rn(v.x), __float2bfloat16_rn(v.y), __float2bfloat16_rn(v.z), __float2bfloat16_rn(v.w)};
+    reinterpret_cast<uint2*>(y)[i] = *reinterpret_cast<const uint2*>(h);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -555,6 +564,13 @@ extern "C" int sd3d_layernorm_cast(const float* x, const float* weight, const fl
     if (x == nullptr || (y_f32 == nullptr && y_bf16 == nullptr)) {
         set_error("sd3d_layernorm_cast: null input or no output");
         return SD3D_ERR_ARG;
+    }
+    if (!normalize && weight == nullptr && bias == nullptr && y_f32 == nullptr && d % 4 == 0 && aligned16(x) &&
+        (reinterpret_cast<uintptr_t>(y_bf16) & 7) == 0) {  // the plain operand cast: vectorised
+        const int64_t quads = (int64_t)n * d / 4;
+        cast_bf16_kernel<<<(unsigned)ceil_div64(quads, 256), 256, 0, (cudaStream_t)stream_>>>(x, quads,
+                                                                                             static_cast<__nv_bfloat16*>(y_bf16));
+        return check_launch("sd3d_layernorm_cast");
     }
     layernorm_cast_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(x, weight, bias, n, d, eps, normalize, y_f32,
                                                                           static_cast<__nv_bfloat16*>(y_bf16));
@@ -661,4 +677,54 @@ extern "C" int sd3d_split_bf16(const float* x, int n, int d, void* y_split, void
     split_bf16_kernel<<<(unsigned)ceil_div64(quads, 256), 256, 0, (cudaStream_t)stream_>>>(
         x, quads, d, static_cast<__nv_bfloat16*>(y_split));
     return check_launch("sd3d_split_bf16");
+}
+
+// fp32 operands in, eval-scale problem: the operand conversion (plain bf16 cast, or the (hi | mid) split for the
+// fp32-tolerance path) and the TMA-fed GEMM behind ONE host call. scratch holds the converted operands (any contents),
+// flags is the zero-filled, self-cleaning workspace of sd3d_mask_logits_bf16 (only used with attn_mask).
+static size_t tm_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" size_t sd3d_mask_logits_large_scratch_bytes(int n, int S, int d, int precision) {
+    if (n <= 0 || S <= 0 || d <= 0) return 0;
+    const size_t per_elem = precision == SD3D_BF16 ? 2 : 4;  // bf16, or two bf16 halves
+    return tm_align_up((size_t)n * d * per_elem, 256) + tm_align_up((size_t)S * d * per_elem, 256);
+}
+
+extern "C" int sd3d_mask_logits_large(const float* q, const float* mf, int n, int S, int d, int precision, float* out,
+                                      float thr, uint8_t* attn_mask, void* scratch, size_t scratch_bytes, void* flags,
+                                      size_t flags_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (precision != SD3D_BF16 && precision != SD3D_F32) {
+        set_error("sd3d_mask_logits_large: precision %d unknown", precision);
+        return SD3D_ERR_UNSUPPORTED;
+    }
+    if (n < 0 || S < 0 || d <= 0) {
+        set_error("sd3d_mask_logits_large: bad shape n=%d S=%d d=%d", n, S, d);
+        return SD3D_ERR_ARG;
+    }
+    if (n == 0 || S == 0) return SD3D_OK;
+    if (d % kTmKB != 0 || d > 256) {
+        set_error("sd3d_mask_logits_large: needs d %% 64 == 0 and d <= 256 (d=%d)", d);
+        return SD3D_ERR_UNSUPPORTED;
+    }
+    if (q == nullptr || mf == nullptr || scratch == nullptr || !aligned16(q) || !aligned16(mf) || !aligned16(scratch) ||
+        scratch_bytes < sd3d_mask_logits_large_scratch_bytes(n, S, d, precision)) {
+        set_error("sd3d_mask_logits_large: null / misaligned operand or scratch < sd3d_mask_logits_large_scratch_bytes()");
+        return SD3D_ERR_ARG;
+    }
+    const bool split = precision == SD3D_F32;
+    const size_t per_elem = split ? 4 : 2;
+    uint8_t* q_conv = static_cast<uint8_t*>(scratch);
+    uint8_t* mf_conv = q_conv + tm_align_up((size_t)n * d * per_elem, 256);
+    if (split) {
+        const int64_t qq = (int64_t)n * d / 4, mq = (int64_t)S * d / 4;
+        split_bf16_kernel<<<(unsigned)ceil_div64(qq, 256), 256, 0, stream>>>(q, qq, d, reinterpret_cast<__nv_bfloat16*>(q_conv));
+        split_bf16_kernel<<<(unsigned)ceil_div64(mq, 256), 256, 0, stream>>>(mf, mq, d, reinterpret_cast<__nv_bfloat16*>(mf_conv));
+    } else {
+        const int64_t qq = (int64_t)n * d / 4, mq = (int64_t)S * d / 4;
+        cast_bf16_kernel<<<(unsigned)ceil_div64(qq, 256), 256, 0, stream>>>(q, qq, reinterpret_cast<__nv_bfloat16*>(q_conv));
+        cast_bf16_kernel<<<(unsigned)ceil_div64(mq, 256), 256, 0, stream>>>(mf, mq, reinterpret_cast<__nv_bfloat16*>(mf_conv));
+    }
+    return launch_tma("sd3d_mask_logits_large", q_conv, mf_conv, n, S, d, split ? 1 : 0, out, thr, attn_mask, flags, flags_bytes,
+                      stream);
 }

@@ -665,6 +665,7 @@ def split_bf16(x: torch.Tensor) -> torch.Tensor:
 
 
 _MASK_WS: dict = {}   # (device index, stream) -> zero-filled row-flag workspace of the TMA mask kernel
+_MASK_SCRATCH: dict = {}   # (device index, stream) -> converted-operand scratch of sd3d_mask_logits_large
 
 
 def mask_logits_bf16(q_bf16: torch.Tensor, mf_bf16: torch.Tensor, threshold: Optional[float] = None, split: bool = False):
@@ -717,15 +718,29 @@ def _mask_logits_raw(q: torch.Tensor, mf: torch.Tensor, code: int, threshold: Op
     if d % 64 == 0 and d <= 256 and ((n + 127) // 128) * ((s + 127) // 128) >= _TMA_MIN_TILES:
         # large problem: convert the operands once (what a fused LayerNorm / x_mask epilogue would hand over), then the
         # TMA-fed tensor-core kernel: plain bf16 operands, or (hi | mid) bf16 pairs for the fp32-tolerance path
-        if code == _lib.BF16:
-            _, q16 = layernorm_cast(q, normalize=False, want_f32=False)
-            _, mf16 = layernorm_cast(mf, normalize=False, want_f32=False)
-            res = mask_logits_bf16(q16, mf16, threshold)
-        else:
-            res = mask_logits_bf16(split_bf16(q), split_bf16(mf), threshold, split=True)
-        if threshold is None:
-            return res, None
-        return res[0], res[1].view(torch.uint8)
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            key = (dev.index, int(torch.cuda.current_stream().cuda_stream))
+            need = int(lib.sd3d_mask_logits_large_scratch_bytes(n, s, d, code))
+            scratch = _MASK_SCRATCH.get(key)
+            if scratch is None or scratch.numel() < need:   # converted operands: one buffer per (device, stream), grown on demand
+                scratch = _MASK_SCRATCH[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+            out = torch.empty(n, s, dtype=torch.float32, device=dev)
+            attn = torch.empty(n, s, dtype=torch.uint8, device=dev) if threshold is not None else None
+            flags, flags_bytes = None, 0
+            if threshold is not None:
+                flags_bytes = int(lib.sd3d_mask_logits_bf16_workspace_bytes(n))
+                flags = _MASK_WS.get(key)
+                if flags is None or flags.numel() < flags_bytes:
+                    flags = _MASK_WS[key] = torch.zeros(max(flags_bytes, 4096), dtype=torch.uint8, device=dev)
+            try:
+                check(lib.sd3d_mask_logits_large(_ptr(q), _ptr(mf), n, s, d, code, _ptr(out),
+                                                 float(threshold) if threshold is not None else 0.0, _ptr(attn), _ptr(scratch),
+                                                 need, _ptr(flags), flags_bytes, _stream()), "sd3d_mask_logits_large")
+            except Exception:
+                _MASK_WS.pop(key, None)
+                raise
+        return out, attn
     with torch.cuda.device(dev):
         out = torch.empty(n, s, dtype=torch.float32, device=dev)
         attn = torch.empty(n, s, dtype=torch.uint8, device=dev) if threshold is not None else None

@@ -141,6 +141,11 @@ def test_mask_head_entries_validate_on_the_host():
     assert lib.sd3d_layernorm_cast(None, None, None, 4, 4096, 1e-5, 1, None, None, None) == _lib.ERR_ARG
     assert lib.sd3d_split_bf16(None, 4, 6, None, None) == _lib.ERR_ARG
     assert lib.sd3d_split_bf16(None, 0, 8, None, None) == _lib.OK
+    assert lib.sd3d_mask_logits_large_scratch_bytes(300, 500, 256, _lib.BF16) == 300 * 256 * 2 + 500 * 256 * 2
+    assert lib.sd3d_mask_logits_large_scratch_bytes(300, 500, 256, _lib.F32) == 300 * 256 * 4 + 500 * 256 * 4
+    assert lib.sd3d_mask_logits_large(None, None, 8, 8, 128, 9, None, 0.0, None, None, 0, None, 0, None) == _lib.ERR_UNSUPPORTED
+    assert lib.sd3d_mask_logits_large(None, None, 8, 8, 96, _lib.BF16, None, 0.0, None, None, 0, None, 0, None) == _lib.ERR_UNSUPPORTED
+    assert lib.sd3d_mask_logits_large(None, None, 8, 8, 128, _lib.BF16, None, 0.0, None, None, 0, None, 0, None) == _lib.ERR_ARG
     for fn, args in ((sd.layernorm_cast, (torch.zeros(2, 8),)), (sd.split_bf16, (torch.zeros(2, 8),)),
                      (sd.mask_logits_bf16, (torch.zeros(2, 64, dtype=torch.bfloat16), torch.zeros(3, 64, dtype=torch.bfloat16)))):
         with pytest.raises(sd.Sd3dError):
