@@ -29,7 +29,7 @@ import dataclasses
 import json
 import os
 import time
-from typing import Callable, Optional, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -40,6 +40,56 @@ def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
     base, rem = divmod(n, world)
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+def balanced_view_bounds(weights: Sequence[float], world: int) -> List[int]:
+    """Contiguous partition of the views into `world` ranges of (nearly) equal total weight -- e.g. visible
+    (point, view) pairs, the unit of gather work -- with at least one view per rank: returns world + 1 boundaries.
+    Trajectory-contiguous ranges keep a rank's views on one part of the scene (fewer rows to exchange, SURVEY 8e-iii);
+    equal weights keep the slowest rank, which sets the pace of every scene, at the mean."""
+    n = len(weights)
+    if world <= 0 or n < world:
+        raise ValueError(f"cannot split {n} views over {world} ranks")
+    total = float(sum(weights))
+    bounds = [0]
+    acc, v = 0.0, 0
+    for r in range(1, world):
+        target = total * r / world
+        # advance while adding the next view keeps us closer to the target; leave enough views for the ranks behind
+        while v < n - (world - r) and (v < bounds[-1] + 1 or acc + 0.5 * float(weights[v]) <= target):
+            acc += float(weights[v])
+            v += 1
+        bounds.append(v)
+    bounds.append(n)
+    return bounds
+
+
+def visible_pair_estimate(xyz: torch.Tensor, K: torch.Tensor, w2c: torch.Tensor, depth: torch.Tensor, device,
+                          tau: float = 0.05, z_near: float = 0.1, max_points: int = 1 << 16, chunk: int = 16) -> torch.Tensor:
+    """Per-view count of visible points on a strided subsample of the scene (placement policy input, set-up time only:
+    plain torch, not the lifting path -- projection + nearest-pixel depth test of SURVEY Appendix A without its exact
+    rounding). Returns int64 [V] on the CPU; identical on every rank that holds the same scene."""
+    n = xyz.shape[0]
+    step = max(1, n // max_points)
+    pts = xyz[::step].to(device=device, dtype=torch.float32)
+    hd, wd = depth.shape[-2:]
+    out = []
+    for v0 in range(0, K.shape[0], chunk):
+        k = K[v0:v0 + chunk].to(device=device, dtype=torch.float32)
+        m = w2c[v0:v0 + chunk].to(device=device, dtype=torch.float32)
+        dmap = depth[v0:v0 + chunk].to(device)
+        dmap = dmap.float() * 0.001 if dmap.dtype == torch.uint16 else dmap.float()
+        cam = torch.einsum("vij,nj->vni", m[:, :, :3], pts) + m[:, None, :, 3]
+        z = cam[..., 2]
+        zs = torch.where(z > z_near, z, torch.ones_like(z))
+        ui = torch.floor(k[:, None, 0] * cam[..., 0] / zs + k[:, None, 2] + 0.5)
+        wi = torch.floor(k[:, None, 1] * cam[..., 1] / zs + k[:, None, 3] + 0.5)
+        ok = (z > z_near) & (ui >= 0) & (ui < wd) & (wi >= 0) & (wi < hd)
+        pix = (wi.clamp(0, hd - 1) * wd + ui.clamp(0, wd - 1)).long()
+        d = torch.gather(dmap.reshape(dmap.shape[0], -1), 1, pix)
+        vis = ok & (d > 0) & ((d - z).abs() <= tau)
+        out.append(vis.sum(dim=1).cpu())
+    return torch.cat(out).to(torch.int64) * step
 
 
 def padded_rows(n: int, world: int) -> int:
@@ -269,14 +319,22 @@ def lift_view_sharded_p2p(xyz: torch.Tensor, K_local: torch.Tensor, w2c_local: t
 
 
 def measure_viewshard(wl: dict, exchange: str, steps: int, warmup: int, rank: int, world: int, dev: torch.device,
-                      variant: int = 0, stage_times: bool = False, pipelined: bool = True):
+                      variant: int = 0, stage_times: bool = False, pipelined: bool = True, balance: bool = True):
     """Times `steps` view-sharded lifts of one scene of workload `wl` on `world` ranks (world == 1: the whole scene
-    on this rank, no exchange). Every rank builds the same scene and keeps its contiguous view range. Device time
+    on this rank, no exchange). Every rank builds the same scene and keeps one contiguous view range (`balance`: ranges of
+    equal estimated visible pairs, else equal view counts). Device time
     with CUDA events, max over ranks. Returns (ms_per_step, n_superpoints, clocks)."""
     from bench import ClockSampler, build_scene
 
     sc = build_scene(wl, 1235, fmap_device=dev)  # identical on every rank (same seeds)
-    vb, ve = shard_range(wl["n_views"], world, rank)
+    if world > 1 and balance and os.environ.get("SD3D_VIEW_BALANCE", "1") != "0":   # (the variable: A/B runs)
+        # placement policy (set-up, before any view's maps exist in a real pipeline): contiguous view ranges of equal
+        # estimated visible pairs instead of equal view counts -- the slowest rank paces every scene
+        est = visible_pair_estimate(sc.xyz, sc.K, sc.w2c, sc.depth, dev)
+        bounds = balanced_view_bounds(est.tolist(), world)
+        vb, ve = bounds[rank], bounds[rank + 1]
+    else:
+        vb, ve = shard_range(wl["n_views"], world, rank)
     d = {k: getattr(sc, k).to(dev) for k in ("xyz", "sp_ids")}
     K_l = sc.K[vb:ve].contiguous().to(dev)
     w2c_l = sc.w2c[vb:ve].contiguous().to(dev)
@@ -376,7 +434,9 @@ def viewshard_report(wl: dict, workload: str, exchange: str, steps: int, warmup:
                     "speedup_vs_1gpu": ms_1 / ms_n, "scaling": "strong",
                     "note": "views of ONE scene sharded over the ranks; p2p = partial rows stored by the gather kernel "
                             "straight into the owner rank's staging buffer over NVLink (sd3d_lift_push), one barrier, "
-                            "owner-side reduce + pooling, one all_reduce of [S,C+1]; two scenes in flight on two CUDA streams"})
+                            "owner-side reduce + pooling, one all_reduce of [S,C+1]; two scenes in flight on two CUDA streams; "
+                            "contiguous view ranges placed so that every rank has the same estimated number of visible "
+                            "(point, view) pairs (depth-only estimate on a point subsample at set-up)"})
     return out
 
 
