@@ -150,7 +150,7 @@ def cpu_reference_step(sc, use_c: bool = True):
     return feat, cnt, sp
 
 
-def cpu_baseline(sc, budget_s: float = 12.0, max_scenes: int = 40):
+def cpu_baseline(sc, budget_s: float = 12.0, max_scenes: int = 200):
     """Times the C/OpenMP port of the oracle (all host threads) on whole scenes of the same workload."""
     import torch
     from oracle import c_ref
